@@ -1,0 +1,639 @@
+// libegx C ABI (include/egx.h): handle, weight hand-off, workspace planning and the forward
+// schedule of the generator (Full_model/Models.py:389-427).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "egx_common.cuh"
+
+using namespace egx;
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr float kBnEps = 1e-5f;    // torch.nn.BatchNorm default; the reference never overrides it
+
+// ---------------------------------------------------------------------------------------------
+// device upload helpers
+// ---------------------------------------------------------------------------------------------
+template <class T>
+T* upload(egx_handle* h, const std::vector<T>& v) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+        return nullptr;
+    h->owned.push_back(p);
+    return static_cast<T*>(p);
+}
+
+const HostTensor* find(egx_handle* h, const std::string& key) {
+    auto it = h->staged.find(key);
+    if (it == h->staged.end()) {
+        h->err = "missing weight: " + key;
+        return nullptr;
+    }
+    return &it->second;
+}
+
+bool need(egx_handle* h, const std::string& key, std::initializer_list<int64_t> shape, const HostTensor** out) {
+    const HostTensor* t = find(h, key);
+    if (!t) return false;
+    if (t->shape != std::vector<int64_t>(shape)) {
+        std::string got, want;
+        for (auto s : t->shape) got += std::to_string(s) + ",";
+        for (auto s : shape) want += std::to_string(s) + ",";
+        h->err = "weight " + key + " has shape (" + got + ") expected (" + want + ")";
+        return false;
+    }
+    *out = t;
+    return true;
+}
+
+// eval-mode BatchNorm -> y = x*scale + shift
+bool fold_bn(egx_handle* h, const std::string& pre, int c, std::vector<float>& scale, std::vector<float>& shift) {
+    const HostTensor *g, *b, *m, *v;
+    if (!need(h, pre + ".weight", {c}, &g) || !need(h, pre + ".bias", {c}, &b) ||
+        !need(h, pre + ".running_mean", {c}, &m) || !need(h, pre + ".running_var", {c}, &v))
+        return false;
+    scale.resize(c);
+    shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        const float s = g->v[i] / std::sqrt(v->v[i] + kBnEps);
+        scale[i] = s;
+        shift[i] = b->v[i] - m->v[i] * s;
+    }
+    return true;
+}
+
+// torch conv weight (cout, cin, kh, kw) -> [cout][kh*kw][cin]
+bool make_conv(egx_handle* h, const std::string& wkey, const std::string* bias_key, const std::string& bnpre,
+               int cin, int cout, int ks, int stride, int relu_first, ConvW* out) {
+    const HostTensor* w;
+    if (!need(h, wkey, {cout, cin, ks, ks}, &w)) return false;
+    const int taps = ks * ks;
+    std::vector<float> packed((size_t)cout * taps * cin);
+    std::vector<__half> packed16(packed.size());
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < taps; ++t) {
+                const float x = w->v[((size_t)o * cin + i) * taps + t];
+                packed[((size_t)o * taps + t) * cin + i] = x;
+                packed16[((size_t)o * taps + t) * cin + i] = __float2half_rn(x);
+            }
+    std::vector<float> scale, shift;
+    if (!fold_bn(h, bnpre, cout, scale, shift)) return false;
+    out->cin = cin; out->cout = cout; out->ks = ks; out->stride = stride; out->relu_first = relu_first;
+    out->w32 = upload(h, packed);
+    out->w16 = upload(h, packed16);
+    out->scale = upload(h, scale);
+    out->shift = upload(h, shift);
+    out->bias = nullptr;
+    if (bias_key) {
+        const HostTensor* b;
+        if (!need(h, *bias_key, {cout}, &b)) return false;
+        out->bias = upload(h, b->v);
+    }
+    return out->w32 && out->w16 && out->scale && out->shift;
+}
+
+bool make_linear(egx_handle* h, const std::string& pre, int in, int out_f, bool bias, LinearW* out) {
+    const HostTensor* w;
+    if (!need(h, pre + ".weight", {out_f, in}, &w)) return false;
+    out->in = in; out->out = out_f;
+    out->w = upload(h, w->v);
+    out->b = nullptr;
+    if (bias) {
+        const HostTensor* b;
+        if (!need(h, pre + ".bias", {out_f}, &b)) return false;
+        out->b = upload(h, b->v);
+    }
+    return out->w != nullptr;
+}
+
+bool make_ln(egx_handle* h, const std::string& pre, int d, LNW* out) {
+    const HostTensor *g, *b;
+    if (!need(h, pre + ".weight", {d}, &g) || !need(h, pre + ".bias", {d}, &b)) return false;
+    out->g = upload(h, g->v);
+    out->b = upload(h, b->v);
+    return out->g && out->b;
+}
+
+bool make_concat_linear(egx_handle* h, std::initializer_list<std::string> pres, int in, int each_out, LinearW* out) {
+    std::vector<float> cat;
+    for (const auto& p : pres) {
+        const HostTensor* w;
+        if (!need(h, p + ".weight", {each_out, in}, &w)) return false;
+        cat.insert(cat.end(), w->v.begin(), w->v.end());
+    }
+    out->in = in; out->out = each_out * (int)pres.size();
+    out->w = upload(h, cat);
+    out->b = nullptr;
+    return out->w != nullptr;
+}
+
+bool make_mha(egx_handle* h, const std::string& pre, const egx_cfg& c, MHAW* m) {
+    const int hk = c.n_head * c.d_k, hv = c.n_head * c.d_v;
+    if (hk != hv) { h->err = "n_head*d_k must equal n_head*d_v"; return false; }
+    return make_linear(h, pre + ".w_qs", c.d_model, hk, false, &m->q) &&
+           make_concat_linear(h, {pre + ".w_ks", pre + ".w_vs"}, c.d_model, hk, &m->kv) &&
+           make_concat_linear(h, {pre + ".w_qs", pre + ".w_ks", pre + ".w_vs"}, c.d_model, hk, &m->qkv) &&
+           make_linear(h, pre + ".fc", hv, c.d_model, false, &m->fc) &&
+           make_ln(h, pre + ".layer_norm", c.d_model, &m->ln);
+}
+
+bool make_ffn(egx_handle* h, const std::string& pre, const egx_cfg& c, FFNW* f) {
+    return make_linear(h, pre + ".w_1", c.d_model, c.d_inner, true, &f->w1) &&
+           make_linear(h, pre + ".w_2", c.d_inner, c.d_model, true, &f->w2) &&
+           make_ln(h, pre + ".layer_norm", c.d_model, &f->ln);
+}
+
+// ---------------------------------------------------------------------------------------------
+// log-mel tables (float64 on the host)
+// ---------------------------------------------------------------------------------------------
+double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+bool build_logmel_tables(egx_handle* h) {
+    const int n_fft = 1024, n_bins = 513, n_mels = 128;
+    std::vector<float> window(n_fft);
+    for (int i = 0; i < n_fft; ++i) window[i] = (float)(0.5 - 0.5 * std::cos(2.0 * kPi * i / n_fft));
+    std::vector<float2> tw512(256), tw1024(513);
+    for (int k = 0; k < 256; ++k)
+        tw512[k] = make_float2((float)std::cos(-2.0 * kPi * k / 512), (float)std::sin(-2.0 * kPi * k / 512));
+    for (int k = 0; k <= 512; ++k)
+        tw1024[k] = make_float2((float)std::cos(-2.0 * kPi * k / 1024), (float)std::sin(-2.0 * kPi * k / 1024));
+    // Slaney mel filterbank, librosa.filters.mel defaults (sr 16000, fmin 0, fmax 8000, norm='slaney')
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(8000.0);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+    std::vector<int> start(n_mels), ptr(n_mels + 1, 0);
+    std::vector<float> wts;
+    for (int m = 0; m < n_mels; ++m) {
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        int first = -1, last = -1;
+        std::vector<double> row(n_bins);
+        for (int k = 0; k < n_bins; ++k) {
+            const double f = 8000.0 * k / (n_bins - 1);
+            const double lower = (f - mel_f[m]) / (mel_f[m + 1] - mel_f[m]);
+            const double upper = (mel_f[m + 2] - f) / (mel_f[m + 2] - mel_f[m + 1]);
+            row[k] = std::max(0.0, std::min(lower, upper)) * enorm;
+            if (row[k] > 0.0) { if (first < 0) first = k; last = k; }
+        }
+        if (first < 0) { first = 0; last = -1; }
+        start[m] = first;
+        for (int k = first; k <= last; ++k) wts.push_back((float)row[k]);
+        ptr[m + 1] = (int)wts.size();
+    }
+    h->lm.window = upload(h, window);
+    h->lm.tw512 = upload(h, tw512);
+    h->lm.tw1024 = upload(h, tw1024);
+    h->lm.mel_start = upload(h, start);
+    h->lm.mel_ptr = upload(h, ptr);
+    h->lm.mel_w = upload(h, wts);
+    return h->lm.window && h->lm.tw512 && h->lm.tw1024 && h->lm.mel_start && h->lm.mel_ptr && h->lm.mel_w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace plan: a bump allocator evaluated identically for sizing and for the forward
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+    size_t off = 0;
+    char* base = nullptr;
+    template <class T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+template <class T>
+struct Slots {
+    T *act[3], *down;
+    float* se_sums;
+    float *fcin, *t0, *spec_feat, *pconv, *prior_feat, *h0, *h1, *h2, *fus_in, *x_a, *x_b, *pre;
+    float *qkv, *attn_o, *hid, *enc_out, *dec_out, *post0, *post1, *post2;
+};
+
+template <class T>
+Slots<T> plan_slots(const egx_handle* h, int B, Plan& p) {
+    const egx_cfg& c = h->cfg;
+    Slots<T> s;
+    const size_t map1 = (size_t)B * h->H[0] * h->W[0] * 32;
+    const size_t map2 = (size_t)B * h->H[1] * h->W[1] * 64;
+    for (auto& a : s.act) a = p.take<T>(map1);
+    s.down = p.take<T>(map2);
+    s.se_sums = p.take<float>((size_t)B * 128);
+    const size_t R = (size_t)B * c.frames;
+    const int hk = c.n_head * c.d_k;
+    s.fcin = p.take<float>(R * h->H[2] * h->W[2]);
+    s.t0 = p.take<float>(R * c.d_model);
+    s.spec_feat = p.take<float>(R * c.d_model);
+    s.pconv = p.take<float>(R * c.pose_dim);
+    s.prior_feat = p.take<float>(R * c.d_model);
+    s.h0 = p.take<float>((size_t)B * c.d_model);
+    s.h1 = p.take<float>((size_t)B * 256);
+    s.h2 = p.take<float>((size_t)B * 64);
+    s.fus_in = p.take<float>(R * c.d_model);
+    s.x_a = p.take<float>(R * c.d_model);
+    s.x_b = p.take<float>(R * c.d_model);
+    s.pre = p.take<float>(R * c.d_model);
+    s.qkv = p.take<float>(R * 3 * hk);
+    s.attn_o = p.take<float>(R * hk);
+    s.hid = p.take<float>(R * c.d_inner);
+    s.enc_out = p.take<float>(R * c.d_model);
+    s.dec_out = p.take<float>(R * c.d_model);
+    s.post0 = p.take<float>(R * 4 * c.d_model);
+    s.post1 = p.take<float>(R * c.d_model);
+    s.post2 = p.take<float>(R * c.pose_dim);
+    return s;
+}
+
+#define LAUNCH(h, expr)                                                        \
+    do {                                                                       \
+        const int _n = (expr);                                                 \
+        if (_n < 0) {                                                          \
+            (h)->err = std::string("launch failed: ") + #expr + ": " +         \
+                       cudaGetErrorString(cudaGetLastError());                 \
+            return 1;                                                          \
+        }                                                                      \
+        (h)->launches += _n;                                                   \
+    } while (0)
+
+int linear(egx_handle* h, const LinearW& w, const float* A, int M, float* C, int relu,
+           const float* addend, int addend_rows, cudaStream_t s) {
+    GemmEpi e;
+    e.bias = w.b; e.relu = relu; e.addend = addend; e.addend_rows = addend_rows; e.addend_ld = w.out;
+    LAUNCH(h, launch_gemm_f32(A, w.in, w.w, M, w.out, w.in, C, w.out, e, s));
+    return 0;
+}
+
+// Runs the trunk; returns the buffer holding the output of `upto` (0 stem, 1..3 layers).
+template <class T>
+int run_trunk(egx_handle* h, const float* spec, int B, Slots<T>& sl, int upto, T** result, cudaStream_t s) {
+    T *x = sl.act[0], *y = sl.act[1], *z = sl.act[2];
+    LAUNCH(h, launch_stem<T>(h->w.stem, spec, B, h->H[0], h->W[0], x, s));
+    *result = x;
+    if (upto == 0) return 0;
+    static const int nblk[3] = {3, 4, 6};
+    int bi = 0;
+    int Hc = h->H[0], Wc = h->W[0];
+    for (int li = 0; li < 3; ++li) {
+        for (int b = 0; b < nblk[li]; ++b, ++bi) {
+            const BlockW& bw = h->w.blocks[bi];
+            const int Ho = h->H[li], Wo = h->W[li];
+            LAUNCH(h, launch_conv_direct<T>(bw.conv1, x, B, Hc, Wc, y, nullptr, s));
+            LAUNCH(h, launch_conv_direct<T>(bw.conv2, y, B, Ho, Wo, z, nullptr, s));
+            EGX_CHECK_CUDA(h, cudaMemsetAsync(sl.se_sums, 0, sizeof(float) * B * bw.se.c, s));
+            LAUNCH(h, launch_se_reduce<T>(z, B, Ho * Wo, bw.se.c, sl.se_sums, s));
+            const T* res = x;
+            if (bw.has_down) {
+                LAUNCH(h, launch_conv_direct<T>(bw.down, x, B, Hc, Wc, sl.down, nullptr, s));
+                res = sl.down;
+            }
+            LAUNCH(h, launch_se_apply<T>(bw.se, z, res, sl.se_sums, B, Ho * Wo, y, s));
+            std::swap(x, y);
+            Hc = Ho; Wc = Wo;
+        }
+        *result = x;
+        if (upto == li + 1) return 0;
+    }
+    return 0;
+}
+
+template <class T>
+int forward_impl(egx_handle* h, const float* spec, const float* prior, const float* sampled, int B,
+                 float* poses, float* emo_feat, float* sem_feat, float* logits, void* ws, size_t ws_bytes,
+                 cudaStream_t s) {
+    const egx_cfg& c = h->cfg;
+    Plan p;
+    p.base = static_cast<char*>(ws);
+    Slots<T> sl = plan_slots<T>(h, B, p);
+    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
+    const Weights& w = h->w;
+    const int R = B * c.frames, d = c.d_model, F = c.frames;
+    const int hk = c.n_head * c.d_k;
+
+    // --- audio encoder (Full_model/Models.py:118-133) ---
+    T* t3 = nullptr;
+    if (run_trunk<T>(h, spec, B, sl, 3, &t3, s)) return 1;
+    LAUNCH(h, launch_conv_direct<T>(w.final_conv, t3, B, h->H[2], h->W[2], nullptr, sl.fcin, s));
+    if (linear(h, w.a_fc1, sl.fcin, R, sl.t0, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.a_fc2, sl.t0, R, sl.spec_feat, 0, nullptr, 0, s)) return 1;
+    // --- prior encoder (Full_model/Models.py:199-212) ---
+    LAUNCH(h, launch_prior_conv(w, prior, B, c.prior_frames, F, c.pose_dim, sl.pconv, s));
+    if (linear(h, w.p_fc1, sl.pconv, R, sl.t0, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.p_fc2, sl.t0, R, sl.prior_feat, 0, nullptr, 0, s)) return 1;
+    // --- emotion / semantic projections, classifier head (Models.py:411-415) ---
+    if (linear(h, w.emo0, sl.spec_feat, R, sl.t0, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.emo2, sl.t0, R, emo_feat, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.sem0, sl.spec_feat, R, sl.t0, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.sem2, sl.t0, R, sem_feat, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.hdr[0], emo_feat, B, sl.h0, 1, nullptr, 0, s)) return 1;
+    if (linear(h, w.hdr[1], sl.h0, B, sl.h1, 1, nullptr, 0, s)) return 1;
+    if (linear(h, w.hdr[2], sl.h1, B, sl.h2, 1, nullptr, 0, s)) return 1;
+    if (linear(h, w.hdr[3], sl.h2, B, logits, 0, nullptr, 0, s)) return 1;
+    // --- fusion (Models.py:417-418; Models_memory.py:551-555) + positional table (Models.py:46-48) ---
+    LAUNCH(h, launch_add(sampled ? sampled : emo_feat, sem_feat, sl.fus_in, (int64_t)R * d, s));
+    if (linear(h, w.fus0, sl.fus_in, R, sl.t0, 1, nullptr, 0, s)) return 1;
+    if (linear(h, w.fus2, sl.t0, R, sl.x_a, 0, w.pos_table, F, s)) return 1;
+    // --- encoder (Models.py:237-260; Layers.py:18-22) ---
+    float* x = sl.x_a;
+    float* x2 = sl.x_b;
+    for (int l = 0; l < c.n_layers; ++l) {
+        const MHAW& a = w.enc_attn[l];
+        const FFNW& f = w.enc_ffn[l];
+        if (linear(h, a.qkv, x, R, sl.qkv, 0, nullptr, 0, s)) return 1;
+        LAUNCH(h, launch_attention(sl.qkv, 3 * hk, sl.qkv + hk, 3 * hk, sl.qkv + 2 * hk, 3 * hk, B, F, F,
+                                   c.n_head, c.d_k, c.d_v, sl.attn_o, hk, s));
+        if (linear(h, a.fc, sl.attn_o, R, sl.pre, 0, x, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, s));
+        if (linear(h, f.w1, x2, R, sl.hid, 1, nullptr, 0, s)) return 1;
+        if (linear(h, f.w2, sl.hid, R, sl.pre, 0, x2, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, l == c.n_layers - 1 ? sl.enc_out : x, s));
+    }
+    // --- decoder (Models.py:279-293; Layers.py:50-58: cross-attention + FFN only) ---
+    const float* dx = sl.prior_feat;
+    for (int l = 0; l < c.n_layers; ++l) {
+        const MHAW& a = w.dec_attn[l];
+        const FFNW& f = w.dec_ffn[l];
+        if (linear(h, a.q, dx, R, sl.qkv, 0, nullptr, 0, s)) return 1;
+        if (linear(h, a.kv, sl.enc_out, R, sl.qkv + (size_t)R * hk, 0, nullptr, 0, s)) return 1;
+        const float* kbuf = sl.qkv + (size_t)R * hk;
+        LAUNCH(h, launch_attention(sl.qkv, hk, kbuf, 2 * hk, kbuf + hk, 2 * hk, B, F, F, c.n_head, c.d_k,
+                                   c.d_v, sl.attn_o, hk, s));
+        if (linear(h, a.fc, sl.attn_o, R, sl.pre, 0, dx, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, s));
+        if (linear(h, f.w1, x2, R, sl.hid, 1, nullptr, 0, s)) return 1;
+        if (linear(h, f.w2, sl.hid, R, sl.pre, 0, x2, 0, s)) return 1;
+        float* out = (l == c.n_layers - 1) ? sl.dec_out : sl.x_a;
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, out, s));
+        dx = out;
+    }
+    // --- pose head (Models.py:352-360,425) ---
+    if (linear(h, w.post[0], sl.dec_out, R, sl.post0, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.post[1], sl.post0, R, sl.post1, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.post[2], sl.post1, R, sl.post2, 0, nullptr, 0, s)) return 1;
+    if (linear(h, w.post[3], sl.post2, R, poses, 0, nullptr, 0, s)) return 1;
+    return 0;
+}
+
+template <class T>
+int get_tap_impl(egx_handle* h, const std::string& name, const void* ws, int B, float* out, size_t cap,
+                        size_t* n_out, cudaStream_t s) {
+    Plan p;
+    p.base = const_cast<char*>(static_cast<const char*>(ws));
+    Slots<T> sl = plan_slots<T>(h, B, p);
+    const egx_cfg& c = h->cfg;
+    const size_t R = (size_t)B * c.frames;
+    const float* src = nullptr;
+    size_t n = 0;
+    if (name == "spectrum_feature") { src = sl.spec_feat; n = R * c.d_model; }
+    else if (name == "prior_feature") { src = sl.prior_feat; n = R * c.d_model; }
+    else if (name == "enc_output") { src = sl.enc_out; n = R * c.d_model; }
+    else if (name == "dec_output") { src = sl.dec_out; n = R * c.d_model; }
+    else if (name == "final_conv") { src = sl.fcin; n = R * h->H[2] * h->W[2]; }
+    else EGX_FAIL(h, "unknown tap: " + name);
+    if (n > cap) EGX_FAIL(h, "tap output buffer too small");
+    EGX_CHECK_CUDA(h, cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    *n_out = n;
+    return 0;
+}
+
+template <class T>
+int debug_trunk_impl(egx_handle* h, const float* spec, int B, int stage, float* out, size_t cap, size_t* n_out,
+                            void* ws, size_t ws_bytes, cudaStream_t s) {
+    Plan p;
+    p.base = static_cast<char*>(ws);
+    Slots<T> sl = plan_slots<T>(h, B, p);
+    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small");
+    T* res = nullptr;
+    if (run_trunk<T>(h, spec, B, sl, stage, &res, s)) return 1;
+    const int li = stage == 0 ? 0 : stage - 1;
+    static const int filt[3] = {32, 64, 128};
+    const int HW = h->H[li] * h->W[li], C = filt[li];
+    const size_t n = (size_t)B * HW * C;
+    if (n > cap) EGX_FAIL(h, "tap output buffer too small");
+    LAUNCH(h, launch_nhwc_to_nchw_f32<T>(res, B, HW, C, out, s));
+    *n_out = n;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int egx_version(void) { return EGX_VERSION; }
+
+int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
+    if (!cfg || !out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return 2;
+    if (cudaSetDevice(device) != cudaSuccess) return 2;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 2;
+    if (prop.major != 10) return 3;   // sm_100a only: no other architecture, no fallback
+    auto* h = new egx_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    const egx_cfg& c = h->cfg;
+    if (c.n_mels != 128 || c.d_model % 32 || c.frames > c.n_position || c.frames > 64 ||
+        c.d_k > 64 || c.d_v > 64) {
+        delete h;
+        return 4;
+    }
+    h->H[0] = c.n_mels; h->W[0] = c.spec_w;
+    for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
+    if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
+    *out = h;
+    return 0;
+}
+
+void egx_destroy(egx_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+}
+
+const char* egx_last_error(const egx_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t egx_launch_count(const egx_handle* h) { return h ? h->launches : 0; }
+
+int egx_set_weight(egx_handle* h, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
+    if (!h || !key || !data) return 1;
+    if (dtype != EGX_DTYPE_F32) return 0;   // num_batches_tracked etc.: nothing to keep
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    t.v.resize((size_t)t.numel());
+    EGX_CHECK_CUDA(h, cudaMemcpy(t.v.data(), data, t.v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    h->staged[key] = std::move(t);
+    h->finalized = false;
+    return 0;
+}
+
+int egx_finalize_weights(egx_handle* h) {
+    if (!h) return 1;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    // drop previously packed weights (keep the log-mel tables: first 6 allocations)
+    for (size_t i = 6; i < h->owned.size(); ++i) cudaFree(h->owned[i]);
+    h->owned.resize(6);
+    h->w = Weights();
+    const egx_cfg& c = h->cfg;
+    Weights& w = h->w;
+    const std::string fe = "audio_encoder.feat_extractor";
+    {
+        const std::string bk = fe + ".conv1.bias";
+        if (!make_conv(h, fe + ".conv1.weight", &bk, fe + ".bn1", 1, 32, 3, 1, 1, &w.stem)) return 1;
+    }
+    static const int nblk[3] = {3, 4, 6}, filt[3] = {32, 64, 128};
+    int cin = 32;
+    for (int li = 0; li < 3; ++li)
+        for (int b = 0; b < nblk[li]; ++b) {
+            const std::string pre = fe + ".layer" + std::to_string(li + 1) + "." + std::to_string(b);
+            const int cout = filt[li], stride = (b == 0 && li > 0) ? 2 : 1;
+            BlockW bw;
+            if (!make_conv(h, pre + ".conv1.weight", nullptr, pre + ".bn1", cin, cout, 3, stride, 1, &bw.conv1)) return 1;
+            if (!make_conv(h, pre + ".conv2.weight", nullptr, pre + ".bn2", cout, cout, 3, 1, 0, &bw.conv2)) return 1;
+            bw.has_down = (stride != 1 || cin != cout);
+            if (bw.has_down &&
+                !make_conv(h, pre + ".downsample.0.weight", nullptr, pre + ".downsample.1", cin, cout, 1, stride, 0, &bw.down))
+                return 1;
+            const int r = cout / 8;
+            const HostTensor *w1, *b1, *w2, *b2;
+            if (!need(h, pre + ".se.fc.0.weight", {r, cout}, &w1) || !need(h, pre + ".se.fc.0.bias", {r}, &b1) ||
+                !need(h, pre + ".se.fc.2.weight", {cout, r}, &w2) || !need(h, pre + ".se.fc.2.bias", {cout}, &b2))
+                return 1;
+            bw.se.c = cout; bw.se.r = r;
+            bw.se.w1 = upload(h, w1->v); bw.se.b1 = upload(h, b1->v);
+            bw.se.w2 = upload(h, w2->v); bw.se.b2 = upload(h, b2->v);
+            w.blocks.push_back(bw);
+            cin = cout;
+        }
+    {
+        const std::string bk = "audio_encoder.final_conv1.bias";
+        if (!make_conv(h, "audio_encoder.final_conv1.weight", &bk, "audio_encoder.bn1", 128, c.frames, 3, 1, 0, &w.final_conv))
+            return 1;
+    }
+    const int d = c.d_model, F = c.frames, P = c.pose_dim, p = c.prior_frames;
+    if (!make_linear(h, "audio_encoder.fc1", h->H[2] * h->W[2], d, true, &w.a_fc1)) return 1;
+    if (!make_linear(h, "audio_encoder.fc2", d, d, true, &w.a_fc2)) return 1;
+    {
+        const HostTensor *c1w, *c1b, *c2w, *c2b;
+        if (!need(h, "prior_seq_encoder.conv1.weight", {F, p, 3}, &c1w) || !need(h, "prior_seq_encoder.conv1.bias", {F}, &c1b) ||
+            !need(h, "prior_seq_encoder.conv2.weight", {F, F, 3}, &c2w) || !need(h, "prior_seq_encoder.conv2.bias", {F}, &c2b))
+            return 1;
+        std::vector<float> s1, t1, s2, t2;
+        if (!fold_bn(h, "prior_seq_encoder.bn1", F, s1, t1) || !fold_bn(h, "prior_seq_encoder.bn2", F, s2, t2)) return 1;
+        w.p_c1w = upload(h, c1w->v); w.p_c1b = upload(h, c1b->v); w.p_s1 = upload(h, s1); w.p_t1 = upload(h, t1);
+        w.p_c2w = upload(h, c2w->v); w.p_c2b = upload(h, c2b->v); w.p_s2 = upload(h, s2); w.p_t2 = upload(h, t2);
+    }
+    if (!make_linear(h, "prior_seq_encoder.fc1", P, d, true, &w.p_fc1)) return 1;
+    if (!make_linear(h, "prior_seq_encoder.fc2", d, d, true, &w.p_fc2)) return 1;
+    if (!make_linear(h, "emotion_proj.0", d, d, true, &w.emo0) || !make_linear(h, "emotion_proj.2", d, d, true, &w.emo2) ||
+        !make_linear(h, "semantic_proj.0", d, d, true, &w.sem0) || !make_linear(h, "semantic_proj.2", d, d, true, &w.sem2) ||
+        !make_linear(h, "fusion_proj.0", d, d, true, &w.fus0) || !make_linear(h, "fusion_proj.2", d, d, true, &w.fus2))
+        return 1;
+    const int hdr_in[4] = {F * d, d, 256, 64}, hdr_out[4] = {d, 256, 64, 8};
+    for (int i = 0; i < 4; ++i)
+        if (!make_linear(h, "emotion_classifer_header." + std::to_string(2 * i), hdr_in[i], hdr_out[i], true, &w.hdr[i])) return 1;
+    const int post_in[4] = {d, 4 * d, d, P}, post_out[4] = {4 * d, d, P, P};
+    for (int i = 0; i < 4; ++i)
+        if (!make_linear(h, "post_projector." + std::to_string(2 * i), post_in[i], post_out[i], true, &w.post[i])) return 1;
+    {
+        const HostTensor* pt;
+        if (!need(h, "encoder.position_enc.pos_table", {1, c.n_position, d}, &pt)) return 1;
+        w.pos_table = upload(h, pt->v);
+    }
+    w.enc_attn.resize(c.n_layers); w.enc_ffn.resize(c.n_layers);
+    w.dec_attn.resize(c.n_layers); w.dec_ffn.resize(c.n_layers);
+    for (int l = 0; l < c.n_layers; ++l) {
+        const std::string e = "encoder.layer_stack." + std::to_string(l), dd = "decoder.layer_stack." + std::to_string(l);
+        if (!make_mha(h, e + ".slf_attn", c, &w.enc_attn[l]) || !make_ffn(h, e + ".pos_ffn", c, &w.enc_ffn[l]) ||
+            !make_mha(h, dd + ".enc_attn", c, &w.dec_attn[l]) || !make_ffn(h, dd + ".pos_ffn", c, &w.dec_ffn[l]))
+            return 1;
+    }
+    for (void* ptr : h->owned)
+        if (!ptr) EGX_FAIL(h, "device allocation failed while packing weights");
+    h->staged.clear();
+    h->finalized = true;
+    return 0;
+}
+
+int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode, int preemph,
+               float* out, void* stream) {
+    if (!h) return 1;
+    if (n_clips <= 0) return 0;
+    if (n_cols < 1 || n_cols > 1 + n_samples / 512) EGX_FAIL(h, "n_cols out of range for n_samples");
+    if (n_cols > 256) EGX_FAIL(h, "n_cols > 256 not supported (shared-memory tile)");
+    if (n_samples < 2) EGX_FAIL(h, "need at least 2 samples");
+    if (mode != EGX_LOGMEL_DB && mode != EGX_LOGMEL_LOG_IN) EGX_FAIL(h, "unknown log-mel mode");
+    LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, (cudaStream_t)stream));
+    return 0;
+}
+
+size_t egx_workspace_bytes(const egx_handle* h, int n_clips) {
+    if (!h || n_clips <= 0) return 0;
+    Plan p;
+    if (h->cfg.precision == EGX_PREC_FP32) plan_slots<float>(h, n_clips, p);
+    else plan_slots<__half>(h, n_clips, p);
+    return p.off + 256;
+}
+
+int egx_generator_forward(egx_handle* h, const float* spec, const float* prior, const float* sampled_emotion,
+                          int n_clips, float* poses, float* emo_feat, float* sem_feat, float* emo_logits,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return 1;
+    if (!h->finalized) EGX_FAIL(h, "weights not finalized");
+    if (n_clips <= 0) return 0;
+    if (!spec || !prior || !poses || !emo_feat || !sem_feat || !emo_logits || !workspace) EGX_FAIL(h, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cfg.precision == EGX_PREC_FP32)
+        return forward_impl<float>(h, spec, prior, sampled_emotion, n_clips, poses, emo_feat, sem_feat, emo_logits,
+                                   workspace, workspace_bytes, s);
+    return forward_impl<__half>(h, spec, prior, sampled_emotion, n_clips, poses, emo_feat, sem_feat, emo_logits,
+                                workspace, workspace_bytes, s);
+}
+
+int egx_get_tap(egx_handle* h, const char* name, const void* workspace, int n_clips, float* out, size_t out_capacity,
+                size_t* n_out, void* stream) {
+    if (!h || !name || !workspace || !out || !n_out) return 1;
+    if (h->cfg.precision == EGX_PREC_FP32)
+        return get_tap_impl<float>(h, name, workspace, n_clips, out, out_capacity, n_out, (cudaStream_t)stream);
+    return get_tap_impl<__half>(h, name, workspace, n_clips, out, out_capacity, n_out, (cudaStream_t)stream);
+}
+
+int egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, float* out, size_t out_capacity,
+                    size_t* n_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !spec || !out || !n_out || !workspace) return 1;
+    if (!h->finalized) EGX_FAIL(h, "weights not finalized");
+    if (stage < 0 || stage > 3) EGX_FAIL(h, "stage must be 0..3");
+    if (h->cfg.precision == EGX_PREC_FP32)
+        return debug_trunk_impl<float>(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
+                                       (cudaStream_t)stream);
+    return debug_trunk_impl<__half>(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
+                                    (cudaStream_t)stream);
+}
+
+int egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim, const double* shift, double* acc,
+                       void* stream) {
+    if (!h || !feats || !acc) return 1;
+    if (dim <= 0) EGX_FAIL(h, "dim must be positive");
+    LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, (cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

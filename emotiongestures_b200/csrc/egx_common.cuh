@@ -1,0 +1,178 @@
+// Shared declarations of libegx (internal).  The public C ABI is include/egx.h.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/egx.h"
+
+namespace egx {
+
+// ---------------------------------------------------------------------------------------------
+// Host-side containers
+// ---------------------------------------------------------------------------------------------
+struct HostTensor {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// One 3x3 (or 1x1) convolution with its folded eval-mode epilogue:
+//   y = (relu_first ? max(acc + bias, 0) : acc + bias) * scale + shift
+struct ConvW {
+    int cin = 0, cout = 0, ks = 3, stride = 1;
+    int relu_first = 0;
+    float* w32 = nullptr;     // [cout][ks*ks][cin] fp32 (K-major: k = tap*cin + ci)
+    __half* w16 = nullptr;    // same, fp16
+    float* bias = nullptr;    // [cout] or null
+    float* scale = nullptr;   // [cout]
+    float* shift = nullptr;   // [cout]
+};
+
+struct LinearW {
+    int in = 0, out = 0;
+    float* w = nullptr;       // [out][in] fp32 (nn.Linear layout == K-major B operand)
+    float* b = nullptr;       // [out] or null
+};
+
+struct LNW { float* g = nullptr; float* b = nullptr; };
+
+struct SEW { int c = 0, r = 0; float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr; };
+
+struct BlockW {
+    ConvW conv1, conv2, down;
+    bool has_down = false;
+    SEW se;
+};
+
+struct MHAW { LinearW q, k, v, kv, qkv, fc; LNW ln; };
+struct FFNW { LinearW w1, w2; LNW ln; };
+
+struct Weights {
+    ConvW stem;                       // 1->32, bias, relu_first, bn
+    std::vector<BlockW> blocks;       // 13 SEBasicBlocks
+    ConvW final_conv;                 // 128->F, bias, bn (no relu)
+    LinearW a_fc1, a_fc2;
+    // prior encoder
+    float *p_c1w = nullptr, *p_c1b = nullptr, *p_s1 = nullptr, *p_t1 = nullptr;
+    float *p_c2w = nullptr, *p_c2b = nullptr, *p_s2 = nullptr, *p_t2 = nullptr;
+    LinearW p_fc1, p_fc2;
+    LinearW emo0, emo2, sem0, sem2, fus0, fus2;
+    LinearW hdr[4];
+    LinearW post[4];
+    float* pos_table = nullptr;       // [n_position][d]
+    std::vector<MHAW> enc_attn, dec_attn;
+    std::vector<FFNW> enc_ffn, dec_ffn;
+};
+
+// Log-mel tables (built in float64 on the host, stored as float32)
+struct LogmelTables {
+    float* window = nullptr;      // [1024] periodic Hann
+    float2* tw512 = nullptr;      // [256] exp(-2*pi*i*k/512)
+    float2* tw1024 = nullptr;     // [513] exp(-2*pi*i*k/1024)
+    int* mel_start = nullptr;     // [128] first bin with non-zero weight
+    int* mel_ptr = nullptr;       // [129] CSR offsets into mel_w
+    float* mel_w = nullptr;       // packed non-zero weights
+};
+
+}  // namespace egx
+
+struct egx_handle {
+    egx_cfg cfg{};
+    int device = 0;
+    std::string err;
+    std::map<std::string, egx::HostTensor> staged;   // weights as received
+    std::vector<void*> owned;                          // device allocations to free
+    egx::Weights w;
+    egx::LogmelTables lm;
+    bool finalized = false;
+    int64_t launches = 0;
+    // trunk geometry
+    int H[4] = {0, 0, 0, 0}, W[4] = {0, 0, 0, 0};      // [0]=input/layer1, [1]=layer2, [2]=layer3
+};
+
+namespace egx {
+
+#define EGX_CHECK_CUDA(h, expr)                                                            \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define EGX_FAIL(h, msg)                                                                   \
+    do {                                                                                   \
+        (h)->err = (msg);                                                                  \
+        return 1;                                                                          \
+    } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Kernel launchers (each returns the number of kernels it enqueued, or <0 on launch error)
+// ---------------------------------------------------------------------------------------------
+int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
+                  int preemph, float* out, cudaStream_t s);
+
+template <class T>
+int launch_stem(const ConvW& c, const float* spec, int B, int H, int W, T* out, cudaStream_t s);
+
+// Direct (CUDA-core) implicit-GEMM convolution over NHWC activations.
+//   out_nchw_f32 != nullptr: write fp32 NCHW there instead of NHWC T (final conv).
+template <class T>
+int launch_conv_direct(const ConvW& c, const T* in, int B, int Hin, int Win, T* out,
+                       float* out_nchw_f32, cudaStream_t s);
+
+template <class T>
+int launch_se_reduce(const T* y, int B, int HW, int C, float* sums, cudaStream_t s);
+
+// out = relu(gate(sums) * y + res), gate = sigmoid(W2 relu(W1 mean + b1) + b2)
+template <class T>
+int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int B, int HW,
+                    T* out, cudaStream_t s);
+
+struct GemmEpi {
+    const float* bias = nullptr;      // [N]
+    int relu = 0;
+    const float* addend = nullptr;    // added after bias/relu; row index = row % addend_rows
+    int addend_rows = 0;              // 0: row index = row
+    int addend_ld = 0;
+};
+// C[M][N] (ldc) = A[M][K] (lda) * W[N][K]^T  (+ epilogue), fp32 CUDA cores
+int launch_gemm_f32(const float* A, int lda, const float* Wt, int M, int N, int K, float* C,
+                    int ldc, const GemmEpi& e, cudaStream_t s);
+
+// out[r] = LayerNorm(x[r]) * g + b   (x already holds the residual sum), eps 1e-6
+int launch_layernorm(const float* x, const LNW& ln, int rows, int d, float* out, cudaStream_t s);
+
+// softmax((q/sqrt(dk)) k^T) v per (clip, head).  q rows: (B*Lq, ldq), k/v rows: (B*Lk, ld*)
+int launch_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                     int B, int Lq, int Lk, int n_head, int dk, int dv, float* out, int ldo,
+                     cudaStream_t s);
+
+int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F, int P,
+                      float* out, cudaStream_t s);
+
+int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t s);
+
+template <class T>
+int launch_nhwc_to_nchw_f32(const T* in, int B, int HW, int C, float* out, cudaStream_t s);
+
+int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
+                          cudaStream_t s);
+
+}  // namespace egx

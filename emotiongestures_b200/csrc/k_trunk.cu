@@ -1,0 +1,351 @@
+// SE-ResNet trunk kernels that are not tensor-core work:
+//   K2  stem: conv3x3 1->32 (+bias) -> ReLU -> BN        Full_model/ResNetSE34V2.py:64-66
+//   K3' direct implicit-GEMM conv on CUDA cores (fp32 arm and fall-back shapes)
+//                                                         Full_model/ResNetBlocks.py:24-30
+//   K4  SE: global mean -> FC/8 -> ReLU -> FC -> sigmoid -> relu(gate*y + residual)
+//                                                         Full_model/ResNetBlocks.py:28-36,92-95
+// Activations are NHWC; T is float (fp32 arm) or __half (tensor-core arm).
+#include "egx_common.cuh"
+
+namespace egx {
+
+namespace {
+
+template <class T> struct Vec4;
+template <> struct Vec4<float> {
+    using type = float4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<__half> {
+    using type = uint2;
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static __device__ __forceinline__ void store(__half* p, const float (&v)[4]) {
+        uint2 t;
+        *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(v[0], v[1]);
+        *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  One thread = one pixel x 4 channels; a
+// warp covers 4 consecutive pixels x 32 channels, so stores are fully coalesced and the nine
+// taps of a pixel are shared through L1.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ spec, int B, int H, int W, const float* __restrict__ w,
+            const float* __restrict__ bias, const float* __restrict__ scale,
+            const float* __restrict__ shift, T* __restrict__ out) {
+    __shared__ float sw[32 * 9], sb[32], ss[32], st[32];
+    for (int i = threadIdx.x; i < 32 * 9; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 32) {
+        sb[threadIdx.x] = bias[threadIdx.x];
+        ss[threadIdx.x] = scale[threadIdx.x];
+        st[threadIdx.x] = shift[threadIdx.x];
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)B * H * W * 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int cg = int(i & 7);
+        const int64_t pix = i >> 3;
+        const int x = int(pix % W);
+        const int y = int((pix / W) % H);
+        const int b = int(pix / ((int64_t)W * H));
+        const float* img = spec + (size_t)b * H * W;
+        float tap[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int yy = y + dy - 1, xx = x + dx - 1;
+                tap[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[yy * W + xx] : 0.f;
+            }
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = cg * 4 + j;
+            float acc = sb[c];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc = fmaf(sw[c * 9 + k], tap[k], acc);
+            v[j] = fmaxf(acc, 0.f) * ss[c] + st[c];
+        }
+        Vec4<T>::store(out + pix * 32 + cg * 4, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3' direct implicit-GEMM convolution (CUDA cores, fp32 accumulate).
+//   M = B*Ho*Wo output pixels, N = cout, K = ks*ks*cin.   Tile 64 x 32 x 32, 128 threads,
+//   4x4 register micro-tile.  Weights [cout][ks*ks][cin] fp32.
+// ------------------------------------------------------------------------------------------
+constexpr int CBM = 64, CBN = 32, CBK = 32;
+
+template <class T>
+__global__ void __launch_bounds__(128)
+conv_direct_kernel(const T* __restrict__ in, int B, int Hin, int Win, int Cin, int Ho, int Wo,
+                   int Cout, int ks, int stride, int pad, const float* __restrict__ w,
+                   const float* __restrict__ bias, const float* __restrict__ scale,
+                   const float* __restrict__ shift, int relu_first, T* __restrict__ out,
+                   float* __restrict__ out_nchw) {
+    __shared__ __align__(16) float As[CBK][CBM + 4];
+    __shared__ __align__(16) float Bs[CBK][CBN + 4];
+    const int tid = threadIdx.x;
+    const int64_t M = (int64_t)B * Ho * Wo;
+    const int64_t m0 = (int64_t)blockIdx.x * CBM;
+    const int n0 = blockIdx.y * CBN;
+    const int tm = tid & 15, tn = tid >> 4;           // 16 x 8 thread grid
+
+    // A loader: thread -> pixel tid/2, 16 consecutive input channels
+    const int lp = tid >> 1, lc = (tid & 1) * 16;
+    const int64_t lm = m0 + lp;
+    const bool lvalid = lm < M;
+    int lb = 0, lho = 0, lwo = 0;
+    if (lvalid) {
+        lwo = int(lm % Wo);
+        lho = int((lm / Wo) % Ho);
+        lb = int(lm / ((int64_t)Wo * Ho));
+    }
+    // B loader: thread -> cout tid/4, 8 consecutive k
+    const int bn = tid >> 2, bk = (tid & 3) * 8;
+    const int K = ks * ks * Cin;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < ks * ks; ++tap) {
+        const int dy = tap / ks, dx = tap % ks;
+        const int hi = lho * stride + dy - pad, wi = lwo * stride + dx - pad;
+        const bool inb = lvalid && hi >= 0 && hi < Hin && wi >= 0 && wi < Win;
+        const T* src = in + (((size_t)lb * Hin + (inb ? hi : 0)) * Win + (inb ? wi : 0)) * Cin;
+        for (int c0 = 0; c0 < Cin; c0 += CBK) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (inb) Vec4<T>::load(src + c0 + lc + q * 4, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) As[lc + q * 4 + j][lp] = v[j];
+            }
+            {
+                const int n = n0 + bn;
+                const float* wsrc = w + (size_t)(n < Cout ? n : 0) * K + tap * Cin + c0 + bk;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Bs[bk + j][bn] = (n < Cout) ? wsrc[j] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < CBK; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + tm * 4 + i;
+        if (m >= M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tn * 4 + j;
+            float t = acc[i][j];
+            if (n < Cout) {
+                if (bias) t += bias[n];
+                if (relu_first) t = fmaxf(t, 0.f);
+                t = t * scale[n] + shift[n];
+            }
+            v[j] = t;
+        }
+        if (out_nchw) {
+            const int wo = int(m % Wo), ho = int((m / Wo) % Ho), b = int(m / ((int64_t)Wo * Ho));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tn * 4 + j;
+                if (n < Cout) out_nchw[(((size_t)b * Cout + n) * Ho + ho) * Wo + wo] = v[j];
+            }
+        } else if (n0 + tn * 4 + 3 < Cout) {
+            Vec4<T>::store(out + m * Cout + n0 + tn * 4, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tn * 4 + j;
+                if (n < Cout) out[m * Cout + n] = T(v[j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4a per-(clip, channel) sums of y (NHWC).  grid (chunks, B); thread -> channel tid % C.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+se_reduce_kernel(const T* __restrict__ y, int HW, int C, int pix_per_block,
+                 float* __restrict__ sums) {
+    __shared__ float red[256];
+    const int b = blockIdx.y;
+    const int c4 = C / 4;                       // threads per pixel (4 channels each)
+    const int lanes = 256 / c4;                 // pixels processed in parallel
+    const int cq = threadIdx.x % c4, pl = threadIdx.x / c4;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* base = y + (size_t)b * HW * C;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+        float v[4];
+        Vec4<T>::load(base + (size_t)p * C + cq * 4, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        red[threadIdx.x] = a[j];
+        __syncthreads();
+        if (pl == 0) {
+            float s = 0.f;
+            for (int l = 0; l < lanes; ++l) s += red[l * c4 + cq];
+            atomicAdd(&sums[(size_t)b * C + cq * 4 + j], s);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4b gate + residual + ReLU.  grid (chunks, B).  Each CTA recomputes the clip's gate (C*C/4
+// MACs) instead of a separate launch: out = relu(gate[c]*y + res).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+se_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, const float* __restrict__ sums,
+                int HW, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2, const float* __restrict__ b2, int pix_per_block,
+                T* __restrict__ out) {
+    __shared__ float mean[128], hid[16], gate[128];
+    const int b = blockIdx.y;
+    if (threadIdx.x < C) mean[threadIdx.x] = sums[(size_t)b * C + threadIdx.x] / (float)HW;
+    __syncthreads();
+    if (threadIdx.x < R) {
+        float a = b1[threadIdx.x];
+        for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], mean[c], a);
+        hid[threadIdx.x] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float a = b2[threadIdx.x];
+        for (int j = 0; j < R; ++j) a = fmaf(w2[threadIdx.x * R + j], hid[j], a);
+        gate[threadIdx.x] = 1.f / (1.f + expf(-a));
+    }
+    __syncthreads();
+    const int c4 = C / 4;
+    const size_t e0 = (size_t)blockIdx.x * pix_per_block * c4;
+    const size_t e1 = min((size_t)HW * c4, e0 + (size_t)pix_per_block * c4);
+    const size_t base = (size_t)b * HW * C;
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int cq = int(e % c4);
+        float vy[4], vr[4], vo[4];
+        Vec4<T>::load(y + base + e * 4, vy);
+        Vec4<T>::load(res + base + e * 4, vr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vo[j] = fmaxf(fmaf(gate[cq * 4 + j], vy[j], vr[j]), 0.f);
+        Vec4<T>::store(out + base + e * 4, vo);
+    }
+}
+
+template <class T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t total, int HW, int C,
+                                    float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = int(i % HW);
+        const int c = int((i / HW) % C);
+        const int64_t b = i / ((int64_t)HW * C);
+        out[i] = float(in[(b * HW + p) * C + c]);
+    }
+}
+
+inline bool ok() { return cudaGetLastError() == cudaSuccess; }
+
+}  // namespace
+
+template <class T>
+int launch_stem(const ConvW& c, const float* spec, int B, int H, int W, T* out, cudaStream_t s) {
+    const int64_t total = (int64_t)B * H * W * 8;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    stem_kernel<T><<<grid, 256, 0, s>>>(spec, B, H, W, c.w32, c.bias, c.scale, c.shift, out);
+    return ok() ? 1 : -1;
+}
+
+template <class T>
+int launch_conv_direct(const ConvW& c, const T* in, int B, int Hin, int Win, T* out,
+                       float* out_nchw_f32, cudaStream_t s) {
+    const int pad = c.ks / 2;
+    const int Ho = (Hin + 2 * pad - c.ks) / c.stride + 1;
+    const int Wo = (Win + 2 * pad - c.ks) / c.stride + 1;
+    const int64_t M = (int64_t)B * Ho * Wo;
+    dim3 grid((unsigned)((M + CBM - 1) / CBM), (unsigned)((c.cout + CBN - 1) / CBN));
+    conv_direct_kernel<T><<<grid, 128, 0, s>>>(in, B, Hin, Win, c.cin, Ho, Wo, c.cout, c.ks,
+                                               c.stride, pad, c.w32, c.bias, c.scale, c.shift,
+                                               c.relu_first, out, out_nchw_f32);
+    return ok() ? 1 : -1;
+}
+
+template <class T>
+int launch_se_reduce(const T* y, int B, int HW, int C, float* sums, cudaStream_t s) {
+    const int ppb = 512;
+    dim3 grid((HW + ppb - 1) / ppb, B);
+    se_reduce_kernel<T><<<grid, 256, 0, s>>>(y, HW, C, ppb, sums);
+    return ok() ? 1 : -1;
+}
+
+template <class T>
+int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int B, int HW,
+                    T* out, cudaStream_t s) {
+    const int ppb = 1024;
+    dim3 grid((HW + ppb - 1) / ppb, B);
+    se_apply_kernel<T><<<grid, 256, 0, s>>>(y, res, sums, HW, se.c, se.r, se.w1, se.b1, se.w2,
+                                            se.b2, ppb, out);
+    return ok() ? 1 : -1;
+}
+
+template <class T>
+int launch_nhwc_to_nchw_f32(const T* in, int B, int HW, int C, float* out, cudaStream_t s) {
+    const int64_t total = (int64_t)B * HW * C;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+    nhwc_to_nchw_kernel<T><<<grid, 256, 0, s>>>(in, total, HW, C, out);
+    return ok() ? 1 : -1;
+}
+
+#define EGX_INST(T)                                                                              \
+    template int launch_stem<T>(const ConvW&, const float*, int, int, int, T*, cudaStream_t);    \
+    template int launch_conv_direct<T>(const ConvW&, const T*, int, int, int, T*, float*,        \
+                                       cudaStream_t);                                            \
+    template int launch_se_reduce<T>(const T*, int, int, int, float*, cudaStream_t);             \
+    template int launch_se_apply<T>(const SEW&, const T*, const T*, const float*, int, int, T*,  \
+                                    cudaStream_t);                                               \
+    template int launch_nhwc_to_nchw_f32<T>(const T*, int, int, int, float*, cudaStream_t);
+EGX_INST(float)
+EGX_INST(__half)
+
+}  // namespace egx

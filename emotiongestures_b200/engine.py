@@ -1,0 +1,178 @@
+"""Object wrapper over the libegx C ABI: weight hand-off, workspace, stream plumbing.
+
+PyTorch is used here for what the reference's host code uses it for — device memory
+(the caching allocator owns every buffer the library touches) and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .config import LOGMEL_LOG_IN, GeneratorConfig
+
+_PREC = {"fp32": _lib.EGX_PREC_FP32, "tc": _lib.EGX_PREC_TC}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One libegx handle bound to one CUDA device (no global state, so DataParallel-style
+    per-replica threads each own an Engine)."""
+
+    def __init__(self, cfg: GeneratorConfig, device, precision: str = "tc"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "emotiongestures_b200 runs on sm_100a CUDA devices only (no CPU fallback); "
+                f"got device {self.device}")
+        if precision not in _PREC:
+            raise ValueError(f"precision must be one of {sorted(_PREC)}")
+        cfg.validate()
+        self.cfg = cfg
+        self.precision = precision
+        self.lib = _lib.load_library()
+        c = _lib.EgxCfg(cfg.frames, cfg.prior_frames, cfg.pose_dim, cfg.d_model, cfg.d_inner,
+                        cfg.n_layers, cfg.n_head, cfg.d_k, cfg.d_v, cfg.n_mels, cfg.spec_w,
+                        cfg.n_position, _PREC[precision])
+        h = C.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        rc = self.lib.egx_create(C.byref(c), index, C.byref(h))
+        if rc != 0:
+            reasons = {2: "bad CUDA device", 3: "device is not compute capability 10.x (sm_100a)",
+                       4: "unsupported geometry", 5: "device allocation failed"}
+            raise RuntimeError(f"egx_create failed: {reasons.get(rc, rc)}")
+        self._h = h
+        self._ws = None
+        self._ws_clips = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.egx_destroy(h)
+
+    # -- helpers ---------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.egx_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, name, shape=None):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        # borrowed caller tensors may be CPU, non-contiguous views or other float types
+        return t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.egx_launch_count(self._h))
+
+    # -- weights ---------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """Hand every float tensor of a reference-layout state_dict to the library."""
+        with torch.cuda.device(self.device):
+            for k, v in sd.items():
+                if not v.is_floating_point():
+                    continue
+                t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                self._check(self.lib.egx_set_weight(self._h, k.encode(), _ptr(t), shape, t.dim(),
+                                                    _lib.EGX_DTYPE_F32), f"egx_set_weight({k})")
+            self._check(self.lib.egx_finalize_weights(self._h), "egx_finalize_weights")
+
+    # -- workspace ---------------------------------------------------------------
+    def workspace(self, n_clips: int):
+        if self._ws is None or n_clips > self._ws_clips:
+            nbytes = int(self.lib.egx_workspace_bytes(self._h, n_clips))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_clips = n_clips
+        return self._ws
+
+    # -- hot path ----------------------------------------------------------------
+    def logmel(self, audio, mode: int = LOGMEL_LOG_IN, preemph: bool = True, n_cols=None):
+        """(B,N) 16 kHz audio -> (B,128,n_cols) log-mel (F1–F4)."""
+        a = self._f32(audio, "audio")
+        if a.dim() != 2:
+            raise RuntimeError("audio must be (B, N)")
+        b, n = a.shape
+        n_cols = self.cfg.spec_w if n_cols is None else int(n_cols)
+        out = torch.empty((b, self.cfg.n_mels, n_cols), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_logmel(self._h, _ptr(a), b, n, n_cols, int(mode),
+                                            int(bool(preemph)), _ptr(out), self._stream()),
+                        "egx_logmel")
+        return out
+
+    def generator_forward(self, spec, prior, sampled_emotion=None):
+        cfg = self.cfg
+        if spec.dim() != 3:
+            raise RuntimeError("input_spectrum must be (B, n_mels, W)")
+        b = spec.shape[0]
+        spec = self._f32(spec, "input_spectrum", (b, cfg.n_mels, cfg.spec_w))
+        prior = self._f32(prior, "prior_seq", (b, cfg.prior_frames, cfg.pose_dim))
+        if sampled_emotion is not None:
+            sampled_emotion = self._f32(sampled_emotion, "sampled_emotion_feature",
+                                        (b, cfg.frames, cfg.d_model))
+        dev = self.device
+        poses = torch.empty((b, cfg.frames, cfg.pose_dim), dtype=torch.float32, device=dev)
+        emo = torch.empty((b, cfg.frames, cfg.d_model), dtype=torch.float32, device=dev)
+        sem = torch.empty_like(emo)
+        logits = torch.empty((b, 8), dtype=torch.float32, device=dev)
+        if b == 0:
+            return poses, emo, sem, logits
+        ws = self.workspace(b)
+        with torch.cuda.device(dev):
+            self._check(self.lib.egx_generator_forward(
+                self._h, _ptr(spec), _ptr(prior), _ptr(sampled_emotion), b, _ptr(poses), _ptr(emo),
+                _ptr(sem), _ptr(logits), _ptr(ws), ws.numel(), self._stream()),
+                "egx_generator_forward")
+        self._last_b = b
+        return poses, emo, sem, logits
+
+    # -- parity probes (tests) ----------------------------------------------------
+    def tap(self, name: str):
+        b = self._last_b
+        cfg = self.cfg
+        out = torch.empty(b * cfg.frames * max(cfg.d_model, cfg.fc1_in), dtype=torch.float32,
+                          device=self.device)
+        n = C.c_size_t()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_get_tap(self._h, name.encode(), _ptr(self._ws), b, _ptr(out),
+                                             out.numel(), C.byref(n), self._stream()), "egx_get_tap")
+        return out[: n.value].view(b, cfg.frames, -1)
+
+    def trunk_stage(self, spec, stage: int):
+        cfg = self.cfg
+        b = spec.shape[0]
+        spec = self._f32(spec, "input_spectrum", (b, cfg.n_mels, cfg.spec_w))
+        ws = self.workspace(b)
+        out = torch.empty(b * cfg.n_mels * cfg.spec_w * 32, dtype=torch.float32, device=self.device)
+        n = C.c_size_t()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_debug_trunk(self._h, _ptr(spec), b, stage, _ptr(out),
+                                                 out.numel(), C.byref(n), _ptr(ws), ws.numel(),
+                                                 self._stream()), "egx_debug_trunk")
+        li = max(stage - 1, 0)
+        c = (32, 64, 128)[li]
+        h, w = cfg.n_mels, cfg.spec_w
+        for _ in range(li):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        return out[: n.value].view(b, c, h, w)
+
+    def fgd_accumulate(self, feats, acc, shift=None):
+        """Add the sufficient statistics of feats (n,D) f32 into acc [1+D+D*D] f64."""
+        f = self._f32(feats, "feats")
+        n, d = f.shape
+        assert acc.dtype == torch.float64 and acc.numel() == 1 + d + d * d and acc.is_cuda
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_fgd_accumulate(self._h, _ptr(f), n, d, _ptr(shift), _ptr(acc),
+                                                    self._stream()), "egx_fgd_accumulate")
+        return acc

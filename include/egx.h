@@ -1,0 +1,121 @@
+/*
+ * libegx — C ABI of the B200-native EmotionGesture generator-inference path.
+ *
+ * The reference (XingqunQi-lab/EmotionGestures) is pure PyTorch and defines no
+ * FFI of its own; its boundary for this path is one nn.Module call,
+ *   pred_pose, _, _, emotion_prediction, _ = generator(in_spec, text, pre_pose, sampled)
+ *   (test_emotion_gesture_diversity_iterative.py:205; Full_model/Models.py:389-427;
+ *    4th argument Full_model/Models_memory.py:521).
+ * The entry points below are what a ctypes binding placed behind that call needs
+ * (INTEGRATION.md shows the stub).  Conventions:
+ *   - extern "C", int status returns (0 = ok, non-zero = error; text via egx_last_error)
+ *   - every data pointer is a DEVICE pointer owned by the caller (e.g. the torch
+ *     allocator); the library never frees or keeps them past the call, except weights,
+ *     which egx_set_weight copies
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); the
+ *     library does not synchronise it (weight loading is the one exception)
+ *   - no global state: one handle per device / per replica thread
+ */
+#ifndef EGX_H
+#define EGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGX_VERSION 1
+
+#if defined(__GNUC__)
+#define EGX_API __attribute__((visibility("default")))
+#else
+#define EGX_API
+#endif
+
+typedef struct egx_handle egx_handle;
+
+/* Geometry of the generator: literals of the constructor call
+ * (test_emotion_gesture_diversity_iterative.py:135; Full_model/Models.py:298-301). */
+typedef struct egx_cfg {
+    int32_t frames;        /* F: 34 (TED) / 60 (BEAT)                         */
+    int32_t prior_frames;  /* p: 4 / 10                                       */
+    int32_t pose_dim;      /* P: 126 / 282                                    */
+    int32_t d_model;       /* d: 256 / 512                                    */
+    int32_t d_inner;       /* FFN hidden: 1024 / 2048                         */
+    int32_t n_layers;      /* 3                                               */
+    int32_t n_head;        /* 8                                               */
+    int32_t d_k;           /* 64                                              */
+    int32_t d_v;           /* 64                                              */
+    int32_t n_mels;        /* 128                                             */
+    int32_t spec_w;        /* spectrogram columns W: 70 / 124                 */
+    int32_t n_position;    /* rows of encoder.position_enc.pos_table: 60      */
+    int32_t precision;     /* EGX_PREC_*                                      */
+} egx_cfg;
+
+enum { EGX_PREC_FP32 = 0,  /* CUDA-core fp32 everywhere (bit-faithful debugging arm)      */
+       EGX_PREC_TC   = 1   /* tcgen05: fp16 operands in the trunk, tf32 in the GEMM chain */ };
+
+enum { EGX_DTYPE_F32 = 0, EGX_DTYPE_I64 = 1 };
+
+enum { EGX_LOGMEL_DB = 0,      /* utils/data_utils.py:36-37 (power_to_db, ref=max)          */
+       EGX_LOGMEL_LOG_IN = 1   /* model/ResNetSE34V2.py:96-98 (log(x+1e-6), InstanceNorm1d) */ };
+
+EGX_API int  egx_version(void);
+
+/* Replaces: Transformer.__init__ (Full_model/Models.py:298-383) as far as device state goes. */
+EGX_API int  egx_create(const egx_cfg* cfg, int device, egx_handle** out);
+EGX_API void egx_destroy(egx_handle* h);
+EGX_API const char* egx_last_error(const egx_handle* h);
+
+/* Replaces: nn.Module.load_state_dict for the keys of SURVEY.md §8(b).  `key` is the
+ * state_dict key, `data` a device pointer to a contiguous tensor.  Unknown keys (text
+ * encoder, never-run modules) are accepted and ignored.  egx_finalize_weights folds
+ * eval-mode BatchNorm into scale/shift, repacks conv weights K-major and uploads. */
+EGX_API int  egx_set_weight(egx_handle* h, const char* key, const void* data, const int64_t* shape,
+                    int ndim, int dtype);
+EGX_API int  egx_finalize_weights(egx_handle* h);
+
+/* Replaces: PreEmphasis.forward (model/utils.py:33-38) + librosa.feature.melspectrogram /
+ * power_to_db (utils/data_utils.py:35-39) or the log+InstanceNorm recipe
+ * (model/ResNetSE34V2.py:96-98).  audio (B,N) f32 -> out (B,128,n_cols) f32. */
+EGX_API int  egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols,
+                int mode, int preemph, float* out, void* stream);
+
+/* Scratch the forward needs for a batch of n_clips (bytes). */
+EGX_API size_t egx_workspace_bytes(const egx_handle* h, int n_clips);
+
+/* Replaces: Transformer.forward (Full_model/Models.py:389-427) minus the text encoder.
+ * spec (B,128,W) f32; prior (B,p,P) f32; sampled_emotion (B,F,d) f32 or NULL
+ * -> poses (B,F,P), emo_feat (B,F,d), sem_feat (B,F,d), emo_logits (B,8), all f32. */
+EGX_API int  egx_generator_forward(egx_handle* h, const float* spec, const float* prior,
+                           const float* sampled_emotion, int n_clips, float* poses,
+                           float* emo_feat, float* sem_feat, float* emo_logits,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Parity probes (tests only).  egx_get_tap copies an intermediate of the LAST forward out of
+ * `workspace` in the reference's layout (f32; NCHW for maps).  Names: layer3,
+ * spectrum_feature, prior_feature, enc_output, dec_output.  egx_debug_trunk re-runs the
+ * trunk on `spec` up to `stage` (0 = stem, 1..3 = layer1..3) and writes that map as f32
+ * NCHW.  Both return the element count through *n_out. */
+EGX_API int  egx_get_tap(egx_handle* h, const char* name, const void* workspace, int n_clips,
+                 float* out, size_t out_capacity, size_t* n_out, void* stream);
+EGX_API int  egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, float* out,
+                     size_t out_capacity, size_t* n_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Replaces: np.mean / np.cov inputs (test_emotion_gesture_diversity_iterative.py:251-254).
+ * Adds the sufficient statistics of feats (n,D) f32 into acc = [n | sum (D) | gram (D*D)]
+ * (float64, device).  `shift` (D, float64, device, may be NULL) is subtracted from every
+ * row first (provisional mean). */
+EGX_API int  egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim,
+                        const double* shift, double* acc, void* stream);
+
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+EGX_API int64_t egx_launch_count(const egx_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGX_H */

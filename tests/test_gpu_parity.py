@@ -1,0 +1,135 @@
+"""GPU parity: libegx (through the C ABI) vs the oracle / the reference-made golden vectors.
+
+Tolerances (BASELINE.json north_star): max-abs 1e-4 on log-mels; 2e-3 relative on poses for
+the tensor-core arm.  The fp32 arm is held to 2e-5 (fp32 re-association only).
+Metrics: rel_fro = ||a-b||_F / ||b||_F ; rel_max = max|a-b| / max|b|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from emotiongestures_b200 import BEAT, LOGMEL_DB, LOGMEL_LOG_IN, TED
+from oracle import generator as og
+from oracle import logmel as ol
+from oracle import synth
+from tests.helpers import inputs, load_golden, model_and_sd, rel_fro, rel_max
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tc": 2e-3}
+
+
+def _engine(name, seed, precision):
+    from emotiongestures_b200.engine import Engine
+    from tests.helpers import CFGS
+    _, sd = model_and_sd(name, seed)
+    eng = Engine(CFGS[name], "cuda:0", precision=precision)
+    eng.load_state_dict(sd)
+    return eng, sd
+
+
+@pytest.mark.parametrize("mode,name", [(LOGMEL_LOG_IN, "log_in"), (LOGMEL_DB, "db")])
+@pytest.mark.parametrize("cfg", [TED, BEAT], ids=["ted", "beat"])
+def test_logmel_matches_fp64_oracle(cfg, mode, name):
+    eng, _ = _engine("ted", 0, "fp32")
+    audio = synth.synth_audio(5, cfg.n_audio, seed=7)
+    ref = ol.logmel(audio, cfg.spec_w, name)
+    got = eng.logmel(torch.from_numpy(audio), mode, True, n_cols=cfg.spec_w).cpu().double().numpy()
+    err = np.abs(got - ref).max()
+    assert err <= 1e-4, f"log-mel max-abs {err:.3e} > 1e-4"
+
+
+def test_logmel_no_preemph_and_ragged_cols():
+    eng, _ = _engine("ted", 0, "fp32")
+    audio = synth.synth_audio(3, 5000, seed=9)          # 10 STFT frames, short clip
+    for cols in (1, 7, 10):
+        ref = ol.logmel(audio, cols, "db", preemph=False)
+        got = eng.logmel(torch.from_numpy(audio), LOGMEL_DB, False, n_cols=cols).cpu().double().numpy()
+        assert np.abs(got - ref).max() <= 1e-4
+    with pytest.raises(RuntimeError):
+        eng.logmel(torch.from_numpy(audio), LOGMEL_DB, False, n_cols=11)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_trunk_stages_match_oracle(precision):
+    eng, sd = _engine("ted", 0, precision)
+    spec, _, _ = inputs(TED, 3, seed=11)
+    taps = og.Taps()
+    with torch.no_grad():
+        og.audio_encoder(sd, spec.unsqueeze(1), taps)
+    for stage, nm in enumerate(["stem", "layer1", "layer2", "layer3"]):
+        got = eng.trunk_stage(spec, stage).cpu()
+        e = rel_fro(got, taps[nm])
+        assert got.shape == taps[nm].shape
+        assert e <= TOL[precision], f"{nm}: rel_fro {e:.3e}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("gold", ["ted_b2", "ted_b2_emotion", "beat_b1"])
+def test_forward_matches_reference_golden(gold, precision):
+    g = load_golden(gold)
+    name = gold.split("_")[0]
+    from tests.helpers import CFGS
+    cfg = CFGS[name]
+    seed, n, with_emo = int(g["seed"]), int(g["n_clips"]), bool(g["with_emotion"])
+    eng, _ = _engine(name, seed, precision)
+    spec, prior, emo = inputs(cfg, n, seed, with_emo)
+    poses, ef, sf, logits = eng.generator_forward(spec, prior, emo)
+    tol = TOL[precision]
+    for nm, got in (("poses", poses), ("emotion_feature", ef), ("semantic_feature", sf),
+                    ("emotion_logits", logits)):
+        e_f, e_m = rel_fro(got.cpu(), g[nm]), rel_max(got.cpu(), g[nm])
+        assert e_f <= tol and e_m <= 1.5 * tol, f"{nm}: rel_fro {e_f:.3e} rel_max {e_m:.3e}"
+    for nm in ("spectrum_feature", "prior_feature", "enc_output", "dec_output"):
+        e = rel_fro(eng.tap(nm)[0].cpu(), g["tap_" + nm])
+        assert e <= tol, f"tap {nm}: rel_fro {e:.3e}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_forward_matches_oracle_ragged_batches(precision):
+    """Batch sizes that do not fill tiles, and batch-independence of per-clip results."""
+    eng, sd = _engine("ted", 5, precision)
+    spec, prior, _ = inputs(TED, 9, seed=21)
+    with torch.no_grad():
+        ref = og.generator_forward(sd, TED, spec, prior)[0]
+    full = eng.generator_forward(spec, prior)[0].cpu()
+    assert rel_fro(full, ref) <= TOL[precision]
+    for n in (1, 5):
+        part = eng.generator_forward(spec[:n], prior[:n])[0].cpu()
+        assert torch.equal(part, full[:n]), "per-clip result depends on batch size"
+    empty = eng.generator_forward(spec[:0], prior[:0])[0]
+    assert empty.shape == (0, TED.frames, TED.pose_dim)
+
+
+def test_module_forward_and_audio_entry():
+    m, sd = model_and_sd("ted", 0)
+    import copy
+    m = copy.deepcopy(m).cuda().eval()
+    m.precision = "fp32"
+    audio = torch.from_numpy(synth.synth_audio(2, TED.n_audio, seed=3))
+    prior = torch.from_numpy(synth.synth_prior(2, TED.prior_frames, TED.pose_dim, 3))
+    text = torch.zeros(2, 60, dtype=torch.int64, device="cuda")
+    out = m.forward_audio(audio.cuda(), text, prior.cuda()[:, :TED.prior_frames])
+    assert len(out) == 5 and out[0].shape == (2, 34, 126) and out[4].shape == (2, 60, 512)
+    spec = torch.from_numpy(ol.logmel(audio.numpy(), TED.spec_w, "log_in")).float()
+    with torch.no_grad():
+        ref = og.generator_forward(sd, TED, spec, prior)[0]
+    assert rel_fro(out[0].cpu(), ref) <= 1e-4
+    with pytest.raises(RuntimeError):
+        m.train()(spec.cuda(), text, prior.cuda())
+
+
+def test_fgd_statistics_match_numpy():
+    eng, _ = _engine("ted", 0, "fp32")
+    rng = np.random.default_rng(0)
+    for n, d in ((1000, 128), (777, 32), (300, 512)):
+        x = (rng.standard_normal((n, d)) * rng.uniform(0.5, 2, d) + rng.uniform(-1, 1, d)).astype(np.float32)
+        acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+        shift = torch.from_numpy(x[:64].astype(np.float64).mean(0)).cuda()
+        eng.fgd_accumulate(torch.from_numpy(x[:400]), acc, shift)
+        eng.fgd_accumulate(torch.from_numpy(x[400:]), acc, shift)
+        from emotiongestures_b200.fgd import finalize_stats
+        mu, sigma = finalize_stats(acc.cpu(), d, shift.cpu())
+        x64 = x.astype(np.float64)
+        np.testing.assert_allclose(mu, x64.mean(0), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(sigma, np.cov(x64, rowvar=False), rtol=1e-9, atol=1e-12)
