@@ -231,7 +231,8 @@ Slots<T> plan_slots(const egx_handle* h, int B, Plan& p) {
     const size_t map2 = (size_t)B * h->H[1] * h->W[1] * 64;
     for (auto& a : s.act) a = p.take<T>(map1);
     s.down = p.take<T>(map2);
-    s.se_sums = p.take<float>((size_t)B * 128);
+    // partial sums per (clip, tile/chunk, channel); the largest case is layer1 with 128-pixel tiles
+    s.se_sums = p.take<float>((size_t)B * (size_t)(h->H[0] * h->W[0] / 64 + 8) * 32);
     const size_t R = (size_t)B * c.frames;
     const int hk = c.n_head * c.d_k;
     s.fcin = p.take<float>(R * h->H[2] * h->W[2]);
@@ -257,9 +258,24 @@ Slots<T> plan_slots(const egx_handle* h, int B, Plan& p) {
     return s;
 }
 
+// Stage tags follow SURVEY.md §8(d): S1 front-end, S2 stem, S3 trunk convs, S4 SE, S5 projection
+// GEMMs outside the transformer, S6 encoder+decoder, S8 FGD statistics; 0 = other.
+struct StageScope {
+    egx_handle* h;
+    int prev;
+    StageScope(egx_handle* hh, int stage) : h(hh), prev(hh->stage) { h->stage = stage; }
+    ~StageScope() { h->stage = prev; }
+};
+
+// When profiling is on, every launch is bracketed by a CUDA-event pair on the launching stream
+// (read back by egx_profile_read); otherwise this is a plain counted launch.
 #define LAUNCH(h, expr)                                                        \
     do {                                                                       \
+        cudaEvent_t _e0 = nullptr, _e1 = nullptr;                              \
+        const bool _prof = profile_acquire((h), &_e0, &_e1);                   \
+        if (_prof) cudaEventRecord(_e0, s);                                    \
         const int _n = (expr);                                                 \
+        if (_prof) cudaEventRecord(_e1, s);                                    \
         if (_n < 0) {                                                          \
             (h)->err = std::string("launch failed: ") + #expr + ": " +         \
                        cudaGetErrorString(cudaGetLastError());                 \
@@ -267,6 +283,15 @@ Slots<T> plan_slots(const egx_handle* h, int B, Plan& p) {
         }                                                                      \
         (h)->launches += _n;                                                   \
     } while (0)
+
+bool profile_acquire(egx_handle* h, cudaEvent_t* e0, cudaEvent_t* e1) {
+    if (!h->profiling || h->prof_used + 2 > h->prof_events.size()) return false;
+    *e0 = h->prof_events[h->prof_used];
+    *e1 = h->prof_events[h->prof_used + 1];
+    h->prof_stage.push_back(h->stage);
+    h->prof_used += 2;
+    return true;
+}
 
 int linear(egx_handle* h, const LinearW& w, const float* A, int M, float* C, int relu,
            const float* addend, int addend_rows, cudaStream_t s) {
@@ -280,7 +305,10 @@ int linear(egx_handle* h, const LinearW& w, const float* A, int M, float* C, int
 template <class T>
 int run_trunk(egx_handle* h, const float* spec, int B, Slots<T>& sl, int upto, T** result, cudaStream_t s) {
     T *x = sl.act[0], *y = sl.act[1], *z = sl.act[2];
-    LAUNCH(h, launch_stem<T>(h->w.stem, spec, B, h->H[0], h->W[0], x, s));
+    {
+        StageScope sc(h, 2);
+        LAUNCH(h, launch_stem<T>(h->w.stem, spec, B, h->H[0], h->W[0], x, s));
+    }
     *result = x;
     if (upto == 0) return 0;
     static const int nblk[3] = {3, 4, 6};
@@ -290,16 +318,19 @@ int run_trunk(egx_handle* h, const float* spec, int B, Slots<T>& sl, int upto, T
         for (int b = 0; b < nblk[li]; ++b, ++bi) {
             const BlockW& bw = h->w.blocks[bi];
             const int Ho = h->H[li], Wo = h->W[li];
-            LAUNCH(h, launch_conv_direct<T>(bw.conv1, x, B, Hc, Wc, y, nullptr, s));
-            LAUNCH(h, launch_conv_direct<T>(bw.conv2, y, B, Ho, Wo, z, nullptr, s));
-            EGX_CHECK_CUDA(h, cudaMemsetAsync(sl.se_sums, 0, sizeof(float) * B * bw.se.c, s));
-            LAUNCH(h, launch_se_reduce<T>(z, B, Ho * Wo, bw.se.c, sl.se_sums, s));
             const T* res = x;
-            if (bw.has_down) {
-                LAUNCH(h, launch_conv_direct<T>(bw.down, x, B, Hc, Wc, sl.down, nullptr, s));
-                res = sl.down;
+            {
+                StageScope sc(h, 3);
+                LAUNCH(h, launch_conv_direct<T>(bw.conv1, x, B, Hc, Wc, y, nullptr, s));
+                LAUNCH(h, launch_conv_direct<T>(bw.conv2, y, B, Ho, Wo, z, nullptr, s));
+                if (bw.has_down) {
+                    LAUNCH(h, launch_conv_direct<T>(bw.down, x, B, Hc, Wc, sl.down, nullptr, s));
+                    res = sl.down;
+                }
             }
-            LAUNCH(h, launch_se_apply<T>(bw.se, z, res, sl.se_sums, B, Ho * Wo, y, s));
+            StageScope sc(h, 4);
+            LAUNCH(h, launch_se_reduce<T>(z, B, Ho * Wo, bw.se.c, sl.se_sums, s));
+            LAUNCH(h, launch_se_apply<T>(bw.se, z, res, sl.se_sums, se_partials(Ho * Wo), B, Ho * Wo, y, s));
             std::swap(x, y);
             Hc = Ho; Wc = Wo;
         }
@@ -325,7 +356,11 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
     // --- audio encoder (Full_model/Models.py:118-133) ---
     T* t3 = nullptr;
     if (run_trunk<T>(h, spec, B, sl, 3, &t3, s)) return 1;
-    LAUNCH(h, launch_conv_direct<T>(w.final_conv, t3, B, h->H[2], h->W[2], nullptr, sl.fcin, s));
+    {
+        StageScope sc(h, 3);
+        LAUNCH(h, launch_conv_direct<T>(w.final_conv, t3, B, h->H[2], h->W[2], nullptr, sl.fcin, s));
+    }
+    StageScope sc5(h, 5);
     if (linear(h, w.a_fc1, sl.fcin, R, sl.t0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.a_fc2, sl.t0, R, sl.spec_feat, 0, nullptr, 0, s)) return 1;
     // --- prior encoder (Full_model/Models.py:199-212) ---
@@ -346,6 +381,7 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
     if (linear(h, w.fus0, sl.fus_in, R, sl.t0, 1, nullptr, 0, s)) return 1;
     if (linear(h, w.fus2, sl.t0, R, sl.x_a, 0, w.pos_table, F, s)) return 1;
     // --- encoder (Models.py:237-260; Layers.py:18-22) ---
+    StageScope sc6(h, 6);
     float* x = sl.x_a;
     float* x2 = sl.x_b;
     for (int l = 0; l < c.n_layers; ++l) {
@@ -379,6 +415,7 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
         dx = out;
     }
     // --- pose head (Models.py:352-360,425) ---
+    StageScope sc5b(h, 5);
     if (linear(h, w.post[0], sl.dec_out, R, sl.post0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.post[1], sl.post0, R, sl.post1, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.post[2], sl.post1, R, sl.post2, 0, nullptr, 0, s)) return 1;
@@ -465,6 +502,7 @@ void egx_destroy(egx_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->owned) cudaFree(p);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     delete h;
 }
 
@@ -581,7 +619,9 @@ int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, in
     if (n_cols > 256) EGX_FAIL(h, "n_cols > 256 not supported (shared-memory tile)");
     if (n_samples < 2) EGX_FAIL(h, "need at least 2 samples");
     if (mode != EGX_LOGMEL_DB && mode != EGX_LOGMEL_LOG_IN) EGX_FAIL(h, "unknown log-mel mode");
-    LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    StageScope sc(h, 1);
+    LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, s));
     return 0;
 }
 
@@ -628,11 +668,45 @@ int egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, fl
                                     (cudaStream_t)stream);
 }
 
+int egx_profile_enable(egx_handle* h, int max_launches) {
+    if (!h) return 1;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    h->profiling = max_launches > 0;
+    h->prof_used = 0;
+    h->prof_stage.clear();
+    while (h->profiling && h->prof_events.size() < (size_t)max_launches * 2) {
+        cudaEvent_t e;
+        EGX_CHECK_CUDA(h, cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+    }
+    return 0;
+}
+
+int egx_profile_read(egx_handle* h, double* ms_per_stage, int64_t* launches_per_stage, int n_stages) {
+    if (!h || !ms_per_stage || !launches_per_stage) return 1;
+    for (int i = 0; i < n_stages; ++i) { ms_per_stage[i] = 0.0; launches_per_stage[i] = 0; }
+    for (size_t i = 0; i < h->prof_stage.size(); ++i) {
+        cudaEvent_t e0 = h->prof_events[2 * i], e1 = h->prof_events[2 * i + 1];
+        EGX_CHECK_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        EGX_CHECK_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const int st = h->prof_stage[i];
+        if (st >= 0 && st < n_stages) { ms_per_stage[st] += ms; launches_per_stage[st] += 1; }
+    }
+    h->prof_used = 0;
+    h->prof_stage.clear();
+    return 0;
+}
+
 int egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim, const double* shift, double* acc,
                        void* stream) {
-    if (!h || !feats || !acc) return 1;
-    if (dim <= 0) EGX_FAIL(h, "dim must be positive");
-    LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, (cudaStream_t)stream));
+    if (!h) return 1;
+    if (n_rows == 0) return 0;      // empty shard: nothing to add
+    if (!feats || !acc) EGX_FAIL(h, "null pointer argument");
+    if (dim <= 0 || n_rows < 0) EGX_FAIL(h, "dim must be positive and n_rows non-negative");
+    cudaStream_t s = (cudaStream_t)stream;
+    StageScope sc(h, 8);
+    LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, s));
     return 0;
 }
 

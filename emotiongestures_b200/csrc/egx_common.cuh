@@ -99,6 +99,12 @@ struct egx_handle {
     egx::LogmelTables lm;
     bool finalized = false;
     int64_t launches = 0;
+    // per-launch CUDA-event profiling (egx_profile_enable / egx_profile_read)
+    bool profiling = false;
+    int stage = 0;
+    size_t prof_used = 0;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_stage;
     // trunk geometry
     int H[4] = {0, 0, 0, 0}, W[4] = {0, 0, 0, 0};      // [0]=input/layer1, [1]=layer2, [2]=layer3
 };
@@ -137,13 +143,16 @@ template <class T>
 int launch_conv_direct(const ConvW& c, const T* in, int B, int Hin, int Win, T* out,
                        float* out_nchw_f32, cudaStream_t s);
 
+// sums: [B][se_partials(HW)][C] partial sums in a fixed order (no atomics: deterministic)
+constexpr int kSePixPerBlock = 512;
+inline int se_partials(int HW) { return (HW + kSePixPerBlock - 1) / kSePixPerBlock; }
 template <class T>
 int launch_se_reduce(const T* y, int B, int HW, int C, float* sums, cudaStream_t s);
 
 // out = relu(gate(sums) * y + res), gate = sigmoid(W2 relu(W1 mean + b1) + b2)
 template <class T>
-int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int B, int HW,
-                    T* out, cudaStream_t s);
+int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int n_part, int B,
+                    int HW, T* out, cudaStream_t s);
 
 struct GemmEpi {
     const float* bias = nullptr;      // [N]

@@ -198,7 +198,9 @@ conv_direct_kernel(const T* __restrict__ in, int B, int Hin, int Win, int Cin, i
 }
 
 // ------------------------------------------------------------------------------------------
-// K4a per-(clip, channel) sums of y (NHWC).  grid (chunks, B); thread -> channel tid % C.
+// K4a per-(clip, pixel-chunk, channel) partial sums of y (NHWC).  grid (chunks, B).  Partials
+// are stored, not atomically added: the gate kernel sums them in a fixed order, so a clip's
+// result is bit-identical whatever the batch size or GPU count (SURVEY.md §4 iv).
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256)
@@ -226,7 +228,7 @@ se_reduce_kernel(const T* __restrict__ y, int HW, int C, int pix_per_block,
         if (pl == 0) {
             float s = 0.f;
             for (int l = 0; l < lanes; ++l) s += red[l * c4 + cq];
-            atomicAdd(&sums[(size_t)b * C + cq * 4 + j], s);
+            sums[((size_t)b * gridDim.x + blockIdx.x) * C + cq * 4 + j] = s;
         }
         __syncthreads();
     }
@@ -239,12 +241,16 @@ se_reduce_kernel(const T* __restrict__ y, int HW, int C, int pix_per_block,
 template <class T>
 __global__ void __launch_bounds__(256)
 se_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, const float* __restrict__ sums,
-                int HW, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
+                int n_part, int HW, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
                 const float* __restrict__ w2, const float* __restrict__ b2, int pix_per_block,
                 T* __restrict__ out) {
     __shared__ float mean[128], hid[16], gate[128];
     const int b = blockIdx.y;
-    if (threadIdx.x < C) mean[threadIdx.x] = sums[(size_t)b * C + threadIdx.x] / (float)HW;
+    if (threadIdx.x < C) {
+        float t = 0.f;
+        for (int i = 0; i < n_part; ++i) t += sums[((size_t)b * n_part + i) * C + threadIdx.x];
+        mean[threadIdx.x] = t / (float)HW;
+    }
     __syncthreads();
     if (threadIdx.x < R) {
         float a = b1[threadIdx.x];
@@ -313,18 +319,18 @@ int launch_conv_direct(const ConvW& c, const T* in, int B, int Hin, int Win, T* 
 
 template <class T>
 int launch_se_reduce(const T* y, int B, int HW, int C, float* sums, cudaStream_t s) {
-    const int ppb = 512;
+    const int ppb = kSePixPerBlock;
     dim3 grid((HW + ppb - 1) / ppb, B);
     se_reduce_kernel<T><<<grid, 256, 0, s>>>(y, HW, C, ppb, sums);
     return ok() ? 1 : -1;
 }
 
 template <class T>
-int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int B, int HW,
-                    T* out, cudaStream_t s) {
+int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int n_part, int B,
+                    int HW, T* out, cudaStream_t s) {
     const int ppb = 1024;
     dim3 grid((HW + ppb - 1) / ppb, B);
-    se_apply_kernel<T><<<grid, 256, 0, s>>>(y, res, sums, HW, se.c, se.r, se.w1, se.b1, se.w2,
+    se_apply_kernel<T><<<grid, 256, 0, s>>>(y, res, sums, n_part, HW, se.c, se.r, se.w1, se.b1, se.w2,
                                             se.b2, ppb, out);
     return ok() ? 1 : -1;
 }
@@ -342,8 +348,8 @@ int launch_nhwc_to_nchw_f32(const T* in, int B, int HW, int C, float* out, cudaS
     template int launch_conv_direct<T>(const ConvW&, const T*, int, int, int, T*, float*,        \
                                        cudaStream_t);                                            \
     template int launch_se_reduce<T>(const T*, int, int, int, float*, cudaStream_t);             \
-    template int launch_se_apply<T>(const SEW&, const T*, const T*, const float*, int, int, T*,  \
-                                    cudaStream_t);                                               \
+    template int launch_se_apply<T>(const SEW&, const T*, const T*, const float*, int, int, int, \
+                                    T*, cudaStream_t);                                               \
     template int launch_nhwc_to_nchw_f32<T>(const T*, int, int, int, float*, cudaStream_t);
 EGX_INST(float)
 EGX_INST(__half)

@@ -75,6 +75,20 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.egx_launch_count(self._h))
 
+    N_STAGES = 9
+    STAGE_NAMES = ("other", "S1_frontend", "S2_stem", "S3_trunk_conv", "S4_se", "S5_proj_gemm",
+                   "S6_enc_dec", "S7", "S8_fgd")
+
+    def profile_enable(self, max_launches: int):
+        self._check(self.lib.egx_profile_enable(self._h, int(max_launches)), "egx_profile_enable")
+
+    def profile_read(self):
+        """{stage: (milliseconds, launches)} of everything recorded since profile_enable."""
+        ms = (C.c_double * self.N_STAGES)()
+        cnt = (C.c_int64 * self.N_STAGES)()
+        self._check(self.lib.egx_profile_read(self._h, ms, cnt, self.N_STAGES), "egx_profile_read")
+        return {self.STAGE_NAMES[i]: (ms[i], int(cnt[i])) for i in range(self.N_STAGES) if cnt[i]}
+
     # -- weights ---------------------------------------------------------------
     def load_state_dict(self, sd):
         """Hand every float tensor of a reference-layout state_dict to the library."""

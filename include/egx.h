@@ -112,6 +112,15 @@ EGX_API int  egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int 
 EGX_API int  egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim,
                         const double* shift, double* acc, void* stream);
 
+/* Measurement hooks (bench.py): with profiling enabled (max_launches > 0) every kernel launch is
+ * bracketed by a CUDA-event pair on the launching stream, tagged with its stage of SURVEY.md
+ * §8(d) (1 front-end, 2 stem, 3 trunk convolutions, 4 SE gate/apply, 5 projection GEMMs,
+ * 6 encoder+decoder, 8 FGD statistics, 0 other).  egx_profile_read waits for the recorded
+ * events, sums elapsed milliseconds and launch counts per stage and resets the recording. */
+EGX_API int  egx_profile_enable(egx_handle* h, int max_launches);
+EGX_API int  egx_profile_read(egx_handle* h, double* ms_per_stage, int64_t* launches_per_stage,
+                      int n_stages);
+
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 EGX_API int64_t egx_launch_count(const egx_handle* h);
 
