@@ -39,6 +39,8 @@ PROTOTYPES = {
                                   C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.c_void_p]),
     "egx_fgd_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "egx_debug_linear_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "egx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "egx_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "egx_launch_count": (C.c_int64, [C.c_void_p]),

@@ -494,6 +494,7 @@ int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
     h->H[0] = c.n_mels; h->W[0] = c.spec_w;
     for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
     if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
+    if (gemm_tc_init_device() != 0) { egx_destroy(h); return 6; }
     *out = h;
     return 0;
 }
@@ -666,6 +667,26 @@ int egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, fl
                                        (cudaStream_t)stream);
     return debug_trunk_impl<__half>(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
                                     (cudaStream_t)stream);
+}
+
+int egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias, const float* addend,
+                        int addend_rows, int M, int N, int K, int relu, float* out32, void* stream) {
+    if (!h || !A || !W || !out32) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    const int ldk = (K + 7) / 8 * 8;
+    __half *a16 = nullptr, *w16 = nullptr, *o16 = nullptr;
+    EGX_CHECK_CUDA(h, cudaMalloc(&a16, (size_t)M * ldk * 2));
+    EGX_CHECK_CUDA(h, cudaMalloc(&w16, (size_t)N * ldk * 2));
+    EGX_CHECK_CUDA(h, cudaMalloc(&o16, (size_t)M * N * 2));
+    LAUNCH(h, launch_cvt_pad_f16(A, M, K, K, a16, ldk, s));
+    LAUNCH(h, launch_cvt_pad_f16(W, N, K, K, w16, ldk, s));
+    GemmEpi e;
+    e.bias = bias; e.relu = relu; e.addend = addend; e.addend_rows = addend_rows; e.addend_ld = N;
+    LAUNCH(h, launch_gemm_tc(a16, ldk, w16, ldk, M, N, K, e, out32, N, o16, N, s));
+    EGX_CHECK_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(a16); cudaFree(w16); cudaFree(o16);
+    return 0;
 }
 
 int egx_profile_enable(egx_handle* h, int max_launches) {

@@ -181,6 +181,13 @@ int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream
 template <class T>
 int launch_nhwc_to_nchw_f32(const T* in, int B, int HW, int C, float* out, cudaStream_t s);
 
+// ---- tensor-core arm (tcgen05) ----
+int gemm_tc_init_device();
+int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __half* out, int ld_out, cudaStream_t s);
+// C = A[M][K] (fp16, pitch lda) x W[N][K]^T (fp16, pitch ldw); outputs fp32 and/or fp16 (either may be null)
+int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
+                   float* out32, int ld32, __half* out16, int ld16, cudaStream_t s);
+
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);
 

@@ -181,6 +181,19 @@ class Engine:
             h, w = (h + 1) // 2, (w + 1) // 2
         return out[: n.value].view(b, c, h, w)
 
+    def debug_linear_tc(self, a, w, bias=None, addend=None, addend_rows=0, relu=False):
+        a, w = self._f32(a, "A"), self._f32(w, "W")
+        m, k = a.shape
+        n = w.shape[0]
+        bias = None if bias is None else self._f32(bias, "bias")
+        addend = None if addend is None else self._f32(addend, "addend")
+        out = torch.empty((m, n), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_debug_linear_tc(self._h, _ptr(a), _ptr(w), _ptr(bias), _ptr(addend),
+                                                     int(addend_rows), m, n, k, int(relu), _ptr(out),
+                                                     self._stream()), "egx_debug_linear_tc")
+        return out
+
     def fgd_accumulate(self, feats, acc, shift=None):
         """Add the sufficient statistics of feats (n,D) f32 into acc [1+D+D*D] f64."""
         f = self._f32(feats, "feats")

@@ -112,6 +112,12 @@ EGX_API int  egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int 
 EGX_API int  egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim,
                         const double* shift, double* acc, void* stream);
 
+/* Parity probe of the tcgen05 Linear kernel alone: out = [relu](A W^T + bias) + addend, A (M,K), W (N,K),
+ * out (M,N) f32; operands are rounded to fp16 inside.  Synchronises the stream (test-only). */
+EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias,
+                         const float* addend, int addend_rows, int M, int N, int K, int relu,
+                         float* out32, void* stream);
+
 /* Measurement hooks (bench.py): with profiling enabled (max_launches > 0) every kernel launch is
  * bracketed by a CUDA-event pair on the launching stream, tagged with its stage of SURVEY.md
  * §8(d) (1 front-end, 2 stem, 3 trunk convolutions, 4 SE gate/apply, 5 projection GEMMs,
