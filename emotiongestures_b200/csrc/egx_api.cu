@@ -494,7 +494,7 @@ int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
     h->H[0] = c.n_mels; h->W[0] = c.spec_w;
     for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
     if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
-    if (gemm_tc_init_device() != 0) { egx_destroy(h); return 6; }
+    if (gemm_tc_init_device() != 0 || conv_tc_init_device() != 0) { egx_destroy(h); return 6; }
     *out = h;
     return 0;
 }
@@ -686,6 +686,19 @@ int egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const flo
     LAUNCH(h, launch_gemm_tc(a16, ldk, w16, ldk, M, N, K, e, out32, N, o16, N, s));
     EGX_CHECK_CUDA(h, cudaStreamSynchronize(s));
     cudaFree(a16); cudaFree(w16); cudaFree(o16);
+    return 0;
+}
+
+int egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int cin, const void* w16, int cout,
+                      int ks, int stride, int relu_first, const float* bias, const float* scale,
+                      const float* shift, void* out16, int nchw, void* stream) {
+    if (!h || !in16 || !w16 || !scale || !shift || !out16) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    ConvW c;
+    c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.relu_first = relu_first;
+    c.w16 = const_cast<__half*>(static_cast<const __half*>(w16));
+    c.bias = const_cast<float*>(bias); c.scale = const_cast<float*>(scale); c.shift = const_cast<float*>(shift);
+    LAUNCH(h, launch_conv_tc(c, static_cast<const __half*>(in16), B, H, W, static_cast<__half*>(out16), nchw, s));
     return 0;
 }
 

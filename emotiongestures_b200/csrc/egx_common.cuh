@@ -188,6 +188,11 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s);
 
+int conv_tc_init_device();
+// in: NHWC fp16 (B,Hin,Win,cin); out: NHWC fp16 or (B,cout,Ho*Wo) fp16 when nchw != 0
+int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw,
+                   cudaStream_t s);
+
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);
 

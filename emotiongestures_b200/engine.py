@@ -194,6 +194,26 @@ class Engine:
                                                      self._stream()), "egx_debug_linear_tc")
         return out
 
+    def debug_conv_tc(self, x, w, scale, shift, bias=None, stride=1, relu_first=False, nchw=False):
+        """x (B,Cin,H,W) f32, w (Cout,Cin,ks,ks) f32 -> (B,Cout,Ho,Wo) f32 via the tcgen05 conv kernel."""
+        dev = self.device
+        b, cin, hh, ww = x.shape
+        cout, _, ks, _ = w.shape
+        x16 = x.to(dev).permute(0, 2, 3, 1).contiguous().half()
+        w16 = w.to(dev).permute(0, 2, 3, 1).contiguous().half()          # [cout][kh][kw][cin]
+        pad = ks // 2
+        ho, wo = (hh + 2 * pad - ks) // stride + 1, (ww + 2 * pad - ks) // stride + 1
+        shape = (b, cout, ho * wo) if nchw else (b, ho, wo, cout)
+        out = torch.full(shape, float("nan"), dtype=torch.float16, device=dev)
+        bias = None if bias is None else self._f32(bias, "bias")
+        scale, shift = self._f32(scale, "scale"), self._f32(shift, "shift")
+        with torch.cuda.device(dev):
+            self._check(self.lib.egx_debug_conv_tc(
+                self._h, _ptr(x16), b, hh, ww, cin, _ptr(w16), cout, ks, stride, int(relu_first), _ptr(bias),
+                _ptr(scale), _ptr(shift), _ptr(out), int(nchw), self._stream()), "egx_debug_conv_tc")
+        out = out.float()
+        return out.view(b, cout, ho, wo) if nchw else out.permute(0, 3, 1, 2).contiguous()
+
     def fgd_accumulate(self, feats, acc, shift=None):
         """Add the sufficient statistics of feats (n,D) f32 into acc [1+D+D*D] f64."""
         f = self._f32(feats, "feats")

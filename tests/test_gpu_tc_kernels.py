@@ -33,3 +33,31 @@ def test_linear_tc(eng, m, n, k, epi):
     if addend is not None:
         ref = ref + addend.double()[torch.arange(m) % 34]
     assert rel_max(got, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,h,w,ks,stride,nchw", [
+    (32, 32, 128, 70, 3, 1, False), (64, 64, 64, 35, 3, 1, False), (128, 128, 32, 18, 3, 1, False),
+    (128, 34, 32, 18, 3, 1, True), (128, 60, 32, 31, 3, 1, True), (64, 64, 64, 62, 3, 1, False),
+    (32, 64, 128, 70, 3, 2, False), (64, 128, 64, 35, 3, 2, False), (32, 64, 128, 70, 1, 2, False),
+    (64, 128, 64, 35, 1, 2, False), (32, 32, 9, 5, 3, 1, False)])
+def test_conv_tc(eng, cin, cout, h, w, ks, stride, nchw):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin + cout + h + w + ks + stride)
+    b = 3
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    bias = torch.randn(cout, generator=g) if nchw else None
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    relu_first = not nchw
+    got = eng.debug_conv_tc(x, wt, scale, shift, bias, stride, relu_first, nchw).cpu()
+    ref = F.conv2d(x.half().double(), wt.half().double(), None if bias is None else bias.double(),
+                   stride=stride, padding=ks // 2)
+    if relu_first:
+        ref = ref.clamp_min(0)
+    ref = ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    assert got.shape == ref.shape
+    assert not torch.isnan(got).any(), "unwritten output elements"
+    # output is stored as fp16: half an ulp of the output scale on top of accumulation order
+    assert rel_max(got, ref) <= 1.5e-3
+    assert ((got - ref).abs() <= 1e-3 * ref.abs() + 2e-3).all()
