@@ -96,11 +96,22 @@ bool make_conv(egx_handle* h, const std::string& wkey, const std::string* bias_k
     return out->w32 && out->w16 && out->scale && out->shift;
 }
 
+// fp16 copy with rows padded to a multiple of 8 elements (16-byte TMA pitch)
+void add_f16_copy(egx_handle* h, const std::vector<float>& w, int out_f, int in, LinearW* out) {
+    const int ld = (in + 7) / 8 * 8;
+    std::vector<__half> v((size_t)out_f * ld, __float2half_rn(0.f));
+    for (int o = 0; o < out_f; ++o)
+        for (int i = 0; i < in; ++i) v[(size_t)o * ld + i] = __float2half_rn(w[(size_t)o * in + i]);
+    out->w16 = upload(h, v);
+    out->ldw = ld;
+}
+
 bool make_linear(egx_handle* h, const std::string& pre, int in, int out_f, bool bias, LinearW* out) {
     const HostTensor* w;
     if (!need(h, pre + ".weight", {out_f, in}, &w)) return false;
     out->in = in; out->out = out_f;
     out->w = upload(h, w->v);
+    add_f16_copy(h, w->v, out_f, in, out);
     out->b = nullptr;
     if (bias) {
         const HostTensor* b;
@@ -127,6 +138,7 @@ bool make_concat_linear(egx_handle* h, std::initializer_list<std::string> pres, 
     }
     out->in = in; out->out = each_out * (int)pres.size();
     out->w = upload(h, cat);
+    add_f16_copy(h, cat, out->out, in, out);
     out->b = nullptr;
     return out->w != nullptr;
 }
@@ -364,7 +376,7 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
     if (linear(h, w.a_fc1, sl.fcin, R, sl.t0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.a_fc2, sl.t0, R, sl.spec_feat, 0, nullptr, 0, s)) return 1;
     // --- prior encoder (Full_model/Models.py:199-212) ---
-    LAUNCH(h, launch_prior_conv(w, prior, B, c.prior_frames, F, c.pose_dim, sl.pconv, s));
+    LAUNCH(h, launch_prior_conv<float>(w, prior, B, c.prior_frames, F, c.pose_dim, sl.pconv, c.pose_dim, s));
     if (linear(h, w.p_fc1, sl.pconv, R, sl.t0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.p_fc2, sl.t0, R, sl.prior_feat, 0, nullptr, 0, s)) return 1;
     // --- emotion / semantic projections, classifier head (Models.py:411-415) ---
@@ -388,13 +400,13 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
         const MHAW& a = w.enc_attn[l];
         const FFNW& f = w.enc_ffn[l];
         if (linear(h, a.qkv, x, R, sl.qkv, 0, nullptr, 0, s)) return 1;
-        LAUNCH(h, launch_attention(sl.qkv, 3 * hk, sl.qkv + hk, 3 * hk, sl.qkv + 2 * hk, 3 * hk, B, F, F,
+        LAUNCH(h, launch_attention<float>(sl.qkv, 3 * hk, sl.qkv + hk, 3 * hk, sl.qkv + 2 * hk, 3 * hk, B, F, F,
                                    c.n_head, c.d_k, c.d_v, sl.attn_o, hk, s));
         if (linear(h, a.fc, sl.attn_o, R, sl.pre, 0, x, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, s));
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, nullptr, s));
         if (linear(h, f.w1, x2, R, sl.hid, 1, nullptr, 0, s)) return 1;
         if (linear(h, f.w2, sl.hid, R, sl.pre, 0, x2, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, l == c.n_layers - 1 ? sl.enc_out : x, s));
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, l == c.n_layers - 1 ? sl.enc_out : x, nullptr, s));
     }
     // --- decoder (Models.py:279-293; Layers.py:50-58: cross-attention + FFN only) ---
     const float* dx = sl.prior_feat;
@@ -404,14 +416,14 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
         if (linear(h, a.q, dx, R, sl.qkv, 0, nullptr, 0, s)) return 1;
         if (linear(h, a.kv, sl.enc_out, R, sl.qkv + (size_t)R * hk, 0, nullptr, 0, s)) return 1;
         const float* kbuf = sl.qkv + (size_t)R * hk;
-        LAUNCH(h, launch_attention(sl.qkv, hk, kbuf, 2 * hk, kbuf + hk, 2 * hk, B, F, F, c.n_head, c.d_k,
+        LAUNCH(h, launch_attention<float>(sl.qkv, hk, kbuf, 2 * hk, kbuf + hk, 2 * hk, B, F, F, c.n_head, c.d_k,
                                    c.d_v, sl.attn_o, hk, s));
         if (linear(h, a.fc, sl.attn_o, R, sl.pre, 0, dx, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, s));
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, x2, nullptr, s));
         if (linear(h, f.w1, x2, R, sl.hid, 1, nullptr, 0, s)) return 1;
         if (linear(h, f.w2, sl.hid, R, sl.pre, 0, x2, 0, s)) return 1;
         float* out = (l == c.n_layers - 1) ? sl.dec_out : sl.x_a;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, out, s));
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, out, nullptr, s));
         dx = out;
     }
     // --- pose head (Models.py:352-360,425) ---
@@ -460,6 +472,221 @@ int debug_trunk_impl(egx_handle* h, const float* spec, int B, int stage, float* 
     const size_t n = (size_t)B * HW * C;
     if (n > cap) EGX_FAIL(h, "tap output buffer too small");
     LAUNCH(h, launch_nhwc_to_nchw_f32<T>(res, B, HW, C, out, s));
+    *n_out = n;
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core arm: fp16 operands (NHWC fp16 trunk maps, fp16 GEMM A operands), fp32 accumulation,
+// fp32 residual stream / LayerNorm / outputs
+// ---------------------------------------------------------------------------------------------
+struct TcSlots {
+    __half *act[3], *down;
+    float* se_sums;
+    __half *fcin, *t16, *spec16, *pconv16, *prior16, *emo16, *fus16, *h0, *h1, *h2, *x16, *x1_16, *qkv16, *o16,
+        *hid16, *enc16, *dec16, *post0, *post1, *post2;
+    float *spec_feat, *prior_feat, *x32a, *x32b, *pre, *enc_out, *dec_out;
+    int P8;
+};
+
+TcSlots plan_tc(const egx_handle* h, int B, Plan& p) {
+    const egx_cfg& c = h->cfg;
+    TcSlots s;
+    const size_t map1 = (size_t)B * h->H[0] * h->W[0] * 32;
+    const size_t map2 = (size_t)B * h->H[1] * h->W[1] * 64;
+    for (auto& a : s.act) a = p.take<__half>(map1);
+    s.down = p.take<__half>(map2);
+    s.se_sums = p.take<float>((size_t)B * (size_t)(h->H[0] * h->W[0] / 64 + 8) * 32);
+    const size_t R = (size_t)B * c.frames;
+    const int hk = c.n_head * c.d_k, d = c.d_model;
+    s.P8 = (c.pose_dim + 7) / 8 * 8;
+    s.fcin = p.take<__half>(R * h->H[2] * h->W[2]);
+    s.t16 = p.take<__half>(R * d);
+    s.spec16 = p.take<__half>(R * d);
+    s.pconv16 = p.take<__half>(R * s.P8);
+    s.prior16 = p.take<__half>(R * d);
+    s.emo16 = p.take<__half>(R * d);
+    s.fus16 = p.take<__half>(R * d);
+    s.h0 = p.take<__half>((size_t)B * d);
+    s.h1 = p.take<__half>((size_t)B * 256);
+    s.h2 = p.take<__half>((size_t)B * 64);
+    s.x16 = p.take<__half>(R * d);
+    s.x1_16 = p.take<__half>(R * d);
+    s.qkv16 = p.take<__half>(R * 3 * hk);
+    s.o16 = p.take<__half>(R * hk);
+    s.hid16 = p.take<__half>(R * c.d_inner);
+    s.enc16 = p.take<__half>(R * d);
+    s.dec16 = p.take<__half>(R * d);
+    s.post0 = p.take<__half>(R * 4 * d);
+    s.post1 = p.take<__half>(R * d);
+    s.post2 = p.take<__half>(R * s.P8);
+    s.spec_feat = p.take<float>(R * d);
+    s.prior_feat = p.take<float>(R * d);
+    s.x32a = p.take<float>(R * d);
+    s.x32b = p.take<float>(R * d);
+    s.pre = p.take<float>(R * d);
+    s.enc_out = p.take<float>(R * d);
+    s.dec_out = p.take<float>(R * d);
+    return s;
+}
+
+// out = [relu](A W^T + b) [+ addend]; A fp16 (pitch lda), outputs fp32 and/or fp16 (pitch ld16)
+int linear_tc(egx_handle* h, const LinearW& w, const __half* A, int lda, int M, float* out32, int ld32, __half* out16,
+              int ld16, int relu, const float* addend, int addend_rows, cudaStream_t s) {
+    GemmEpi e;
+    e.bias = w.b; e.relu = relu; e.addend = addend; e.addend_rows = addend_rows; e.addend_ld = w.out;
+    LAUNCH(h, launch_gemm_tc(A, lda, w.w16, w.ldw, M, w.out, w.in, e, out32, ld32, out16, ld16, s));
+    return 0;
+}
+
+int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto, __half** result, cudaStream_t s) {
+    __half *x = sl.act[0], *y = sl.act[1], *z = sl.act[2];
+    {
+        StageScope sc(h, 2);
+        LAUNCH(h, launch_stem<__half>(h->w.stem, spec, B, h->H[0], h->W[0], x, s));
+    }
+    *result = x;
+    if (upto == 0) return 0;
+    static const int nblk[3] = {3, 4, 6};
+    int bi = 0;
+    int Hc = h->H[0], Wc = h->W[0];
+    for (int li = 0; li < 3; ++li) {
+        for (int b = 0; b < nblk[li]; ++b, ++bi) {
+            const BlockW& bw = h->w.blocks[bi];
+            const int Ho = h->H[li], Wo = h->W[li];
+            const __half* res = x;
+            {
+                StageScope sc(h, 3);
+                LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, s));
+                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, s));
+                if (bw.has_down) {
+                    LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, sl.down, 0, s));
+                    res = sl.down;
+                }
+            }
+            StageScope sc(h, 4);
+            LAUNCH(h, launch_se_reduce<__half>(z, B, Ho * Wo, bw.se.c, sl.se_sums, s));
+            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, se_partials(Ho * Wo), B, Ho * Wo, y, s));
+            std::swap(x, y);
+            Hc = Ho; Wc = Wo;
+        }
+        *result = x;
+        if (upto == li + 1) return 0;
+    }
+    return 0;
+}
+
+int forward_tc(egx_handle* h, const float* spec, const float* prior, const float* sampled, int B, float* poses,
+               float* emo_feat, float* sem_feat, float* logits, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const egx_cfg& c = h->cfg;
+    Plan p;
+    p.base = static_cast<char*>(ws);
+    TcSlots sl = plan_tc(h, B, p);
+    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
+    const Weights& w = h->w;
+    const int R = B * c.frames, d = c.d_model, F = c.frames, P = c.pose_dim, P8 = sl.P8;
+    const int hk = c.n_head * c.d_k, HW3 = h->H[2] * h->W[2];
+
+    __half* t3 = nullptr;
+    if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;
+    {
+        StageScope sc(h, 3);
+        LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, s));
+    }
+    StageScope sc5(h, 5);
+    if (linear_tc(h, w.a_fc1, sl.fcin, HW3, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.a_fc2, sl.t16, d, R, sl.spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
+    LAUNCH(h, launch_prior_conv<__half>(w, prior, B, c.prior_frames, F, P, sl.pconv16, P8, s));
+    if (linear_tc(h, w.p_fc1, sl.pconv16, P8, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.p_fc2, sl.t16, d, R, sl.prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.emo0, sl.spec16, d, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.emo2, sl.t16, d, R, emo_feat, d, sl.emo16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.sem0, sl.spec16, d, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.sem2, sl.t16, d, R, sem_feat, d, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.hdr[0], sl.emo16, F * d, B, nullptr, 0, sl.h0, d, 1, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.hdr[1], sl.h0, d, B, nullptr, 0, sl.h1, 256, 1, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.hdr[2], sl.h1, 256, B, nullptr, 0, sl.h2, 64, 1, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.hdr[3], sl.h2, 64, B, logits, 8, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    LAUNCH(h, launch_add_f16(sampled ? sampled : emo_feat, sem_feat, sl.fus16, (int64_t)R * d, s));
+    if (linear_tc(h, w.fus0, sl.fus16, d, R, nullptr, 0, sl.t16, d, 1, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.fus2, sl.t16, d, R, sl.x32a, d, sl.x16, d, 0, w.pos_table, F, s)) return 1;
+
+    StageScope sc6(h, 6);
+    float *x32 = sl.x32a, *y32 = sl.x32b;
+    for (int l = 0; l < c.n_layers; ++l) {
+        const MHAW& a = w.enc_attn[l];
+        const FFNW& f = w.enc_ffn[l];
+        const bool last = l == c.n_layers - 1;
+        if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
+        LAUNCH(h, launch_attention<__half>(sl.qkv16, 3 * hk, sl.qkv16 + hk, 3 * hk, sl.qkv16 + 2 * hk, 3 * hk, B, F, F,
+                                           c.n_head, c.d_k, c.d_v, sl.o16, hk, s));
+        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, x32, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
+        if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, last ? sl.enc_out : x32, last ? sl.enc16 : sl.x16, s));
+    }
+    const float* dx32 = sl.prior_feat;
+    const __half* dx16 = sl.prior16;
+    for (int l = 0; l < c.n_layers; ++l) {
+        const MHAW& a = w.dec_attn[l];
+        const FFNW& f = w.dec_ffn[l];
+        const bool last = l == c.n_layers - 1;
+        __half* kv = sl.qkv16 + (size_t)R * hk;
+        if (linear_tc(h, a.q, dx16, d, R, nullptr, 0, sl.qkv16, hk, 0, nullptr, 0, s)) return 1;
+        if (linear_tc(h, a.kv, sl.enc16, d, R, nullptr, 0, kv, 2 * hk, 0, nullptr, 0, s)) return 1;
+        LAUNCH(h, launch_attention<__half>(sl.qkv16, hk, kv, 2 * hk, kv + hk, 2 * hk, B, F, F, c.n_head, c.d_k, c.d_v,
+                                           sl.o16, hk, s));
+        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, dx32, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
+        if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
+        float* o32 = last ? sl.dec_out : x32;
+        __half* o16 = last ? sl.dec16 : sl.x16;
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, o32, o16, s));
+        dx32 = o32; dx16 = o16;
+    }
+    StageScope sc5b(h, 5);
+    if (linear_tc(h, w.post[0], sl.dec16, d, R, nullptr, 0, sl.post0, 4 * d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.post[1], sl.post0, 4 * d, R, nullptr, 0, sl.post1, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.post[2], sl.post1, d, R, nullptr, 0, sl.post2, P8, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.post[3], sl.post2, P8, R, poses, P, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    return 0;
+}
+
+int get_tap_tc(egx_handle* h, const std::string& name, const void* ws, int B, float* out, size_t cap, size_t* n_out,
+               cudaStream_t s) {
+    Plan p;
+    p.base = const_cast<char*>(static_cast<const char*>(ws));
+    TcSlots sl = plan_tc(h, B, p);
+    const size_t n = (size_t)B * h->cfg.frames * h->cfg.d_model;
+    const float* src = nullptr;
+    if (name == "spectrum_feature") src = sl.spec_feat;
+    else if (name == "prior_feature") src = sl.prior_feat;
+    else if (name == "enc_output") src = sl.enc_out;
+    else if (name == "dec_output") src = sl.dec_out;
+    else EGX_FAIL(h, "unknown tap: " + name);
+    if (n > cap) EGX_FAIL(h, "tap output buffer too small");
+    EGX_CHECK_CUDA(h, cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    *n_out = n;
+    return 0;
+}
+
+int debug_trunk_tc(egx_handle* h, const float* spec, int B, int stage, float* out, size_t cap, size_t* n_out, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
+    Plan p;
+    p.base = static_cast<char*>(ws);
+    TcSlots sl = plan_tc(h, B, p);
+    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small");
+    __half* res = nullptr;
+    if (run_trunk_tc(h, spec, B, sl, stage, &res, s)) return 1;
+    const int li = stage == 0 ? 0 : stage - 1;
+    static const int filt[3] = {32, 64, 128};
+    const int HW = h->H[li] * h->W[li], C = filt[li];
+    const size_t n = (size_t)B * HW * C;
+    if (n > cap) EGX_FAIL(h, "tap output buffer too small");
+    LAUNCH(h, launch_nhwc_to_nchw_f32<__half>(res, B, HW, C, out, s));
     *n_out = n;
     return 0;
 }
@@ -630,7 +857,7 @@ size_t egx_workspace_bytes(const egx_handle* h, int n_clips) {
     if (!h || n_clips <= 0) return 0;
     Plan p;
     if (h->cfg.precision == EGX_PREC_FP32) plan_slots<float>(h, n_clips, p);
-    else plan_slots<__half>(h, n_clips, p);
+    else plan_tc(h, n_clips, p);
     return p.off + 256;
 }
 
@@ -645,8 +872,8 @@ int egx_generator_forward(egx_handle* h, const float* spec, const float* prior, 
     if (h->cfg.precision == EGX_PREC_FP32)
         return forward_impl<float>(h, spec, prior, sampled_emotion, n_clips, poses, emo_feat, sem_feat, emo_logits,
                                    workspace, workspace_bytes, s);
-    return forward_impl<__half>(h, spec, prior, sampled_emotion, n_clips, poses, emo_feat, sem_feat, emo_logits,
-                                workspace, workspace_bytes, s);
+    return forward_tc(h, spec, prior, sampled_emotion, n_clips, poses, emo_feat, sem_feat, emo_logits, workspace,
+                      workspace_bytes, s);
 }
 
 int egx_get_tap(egx_handle* h, const char* name, const void* workspace, int n_clips, float* out, size_t out_capacity,
@@ -654,7 +881,7 @@ int egx_get_tap(egx_handle* h, const char* name, const void* workspace, int n_cl
     if (!h || !name || !workspace || !out || !n_out) return 1;
     if (h->cfg.precision == EGX_PREC_FP32)
         return get_tap_impl<float>(h, name, workspace, n_clips, out, out_capacity, n_out, (cudaStream_t)stream);
-    return get_tap_impl<__half>(h, name, workspace, n_clips, out, out_capacity, n_out, (cudaStream_t)stream);
+    return get_tap_tc(h, name, workspace, n_clips, out, out_capacity, n_out, (cudaStream_t)stream);
 }
 
 int egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, float* out, size_t out_capacity,
@@ -665,8 +892,8 @@ int egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int stage, fl
     if (h->cfg.precision == EGX_PREC_FP32)
         return debug_trunk_impl<float>(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
                                        (cudaStream_t)stream);
-    return debug_trunk_impl<__half>(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
-                                    (cudaStream_t)stream);
+    return debug_trunk_tc(h, spec, n_clips, stage, out, out_capacity, n_out, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
 }
 
 int egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias, const float* addend,

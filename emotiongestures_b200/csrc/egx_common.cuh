@@ -45,6 +45,8 @@ struct LinearW {
     int in = 0, out = 0;
     float* w = nullptr;       // [out][in] fp32 (nn.Linear layout == K-major B operand)
     float* b = nullptr;       // [out] or null
+    __half* w16 = nullptr;    // [out][ldw] fp16, rows padded to a multiple of 8 elements (TMA pitch)
+    int ldw = 0;
 };
 
 struct LNW { float* g = nullptr; float* b = nullptr; };
@@ -166,17 +168,21 @@ int launch_gemm_f32(const float* A, int lda, const float* Wt, int M, int N, int 
                     int ldc, const GemmEpi& e, cudaStream_t s);
 
 // out[r] = LayerNorm(x[r]) * g + b   (x already holds the residual sum), eps 1e-6
-int launch_layernorm(const float* x, const LNW& ln, int rows, int d, float* out, cudaStream_t s);
-
-// softmax((q/sqrt(dk)) k^T) v per (clip, head).  q rows: (B*Lq, ldq), k/v rows: (B*Lk, ld*)
-int launch_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                     int B, int Lq, int Lk, int n_head, int dk, int dv, float* out, int ldo,
+int launch_layernorm(const float* x, const LNW& ln, int rows, int d, float* out, __half* out16,
                      cudaStream_t s);
 
+// softmax((q/sqrt(dk)) k^T) v per (clip, head).  q rows: (B*Lq, ldq), k/v rows: (B*Lk, ld*)
+template <class T>
+int launch_attention(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv,
+                     int B, int Lq, int Lk, int n_head, int dk, int dv, T* out, int ldo,
+                     cudaStream_t s);
+
+template <class T>
 int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F, int P,
-                      float* out, cudaStream_t s);
+                      T* out, int ldo, cudaStream_t s);
 
 int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t s);
+int launch_add_f16(const float* a, const float* b, __half* out, int64_t n, cudaStream_t s);
 
 template <class T>
 int launch_nhwc_to_nchw_f32(const T* in, int B, int HW, int C, float* out, cudaStream_t s);

@@ -97,7 +97,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // One warp per row; d <= 1024.
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                 const float* __restrict__ b, int rows, int d, float* __restrict__ out) {
+                 const float* __restrict__ b, int rows, int d, float* __restrict__ out,
+                 __half* __restrict__ out16) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -108,15 +109,19 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
     float q = 0.f;
     for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
     const float rstd = rsqrtf(warp_sum(q) / d + 1e-6f);
-    for (int c = lane; c < d; c += 32)
-        out[(size_t)row * d + c] = (xr[c] - mean) * rstd * g[c] + b[c];
+    for (int c = lane; c < d; c += 32) {
+        const float y = (xr[c] - mean) * rstd * g[c] + b[c];
+        out[(size_t)row * d + c] = y;
+        if (out16) out16[(size_t)row * d + c] = __float2half_rn(y);
+    }
 }
 
 // One CTA per (head, clip).  Everything in shared memory; L <= 64.
+template <class T>
 __global__ void __launch_bounds__(128)
-attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
-                 const float* __restrict__ v, int ldv, int Lq, int Lk, int dk, int dv,
-                 float scale, float* __restrict__ out, int ldo) {
+attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
+                 const T* __restrict__ v, int ldv, int Lq, int Lk, int dk, int dv,
+                 float scale, T* __restrict__ out, int ldo) {
     extern __shared__ float sm[];
     float* sq = sm;                         // [Lq][dk]
     float* sk = sq + Lq * dk;               // [Lk][dk+1]
@@ -126,15 +131,15 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
     const int tid = threadIdx.x;
     for (int i = tid; i < Lq * dk; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
-        sq[i] = q[((size_t)b * Lq + r) * ldq + h * dk + c] * scale;
+        sq[i] = float(q[((size_t)b * Lq + r) * ldq + h * dk + c]) * scale;
     }
     for (int i = tid; i < Lk * dk; i += blockDim.x) {
         const int r = i / dk, c = i % dk;
-        sk[r * (dk + 1) + c] = k[((size_t)b * Lk + r) * ldk + h * dk + c];
+        sk[r * (dk + 1) + c] = float(k[((size_t)b * Lk + r) * ldk + h * dk + c]);
     }
     for (int i = tid; i < Lk * dv; i += blockDim.x) {
         const int r = i / dv, c = i % dv;
-        sv[i] = v[((size_t)b * Lk + r) * ldv + h * dv + c];
+        sv[i] = float(v[((size_t)b * Lk + r) * ldv + h * dv + c]);
     }
     __syncthreads();
     for (int i = tid; i < Lq * Lk; i += blockDim.x) {
@@ -160,19 +165,20 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
         const int r = i / dv, c = i % dv;
         float a = 0.f;
         for (int t = 0; t < Lk; ++t) a = fmaf(ss[r * (Lk + 1) + t], sv[t * dv + c], a);
-        out[((size_t)b * Lq + r) * ldo + h * dv + c] = a;
+        out[((size_t)b * Lq + r) * ldo + h * dv + c] = T(a);
     }
 }
 
 // Prior-pose encoder front: Conv1d(p->F,k3) -> ReLU -> BN -> Conv1d(F->F,k3) -> ReLU -> BN along
 // the pose axis (channels = frames).  One CTA per clip.
+template <class T>
 __global__ void __launch_bounds__(256)
 prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
                   const float* __restrict__ w1, const float* __restrict__ b1,
                   const float* __restrict__ s1, const float* __restrict__ t1,
                   const float* __restrict__ w2, const float* __restrict__ b2,
                   const float* __restrict__ s2, const float* __restrict__ t2,
-                  float* __restrict__ out) {
+                  T* __restrict__ out, int ldo) {
     extern __shared__ float sm[];
     const int PW = P + 2;
     float* sin_ = sm;                 // [p][P+2] zero-padded
@@ -199,7 +205,7 @@ prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
         for (int c = 0; c < F; ++c)
 #pragma unroll
             for (int k = 0; k < 3; ++k) a = fmaf(w2[(f * F + c) * 3 + k], mid[c * PW + x + k], a);
-        out[((size_t)b * F + f) * P + x] = fmaxf(a, 0.f) * s2[f] + t2[f];
+        out[((size_t)b * F + f) * ldo + x] = T(fmaxf(a, 0.f) * s2[f] + t2[f]);
     }
 }
 
@@ -210,6 +216,19 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
         const float4 x = reinterpret_cast<const float4*>(a)[i];
         const float4 y = reinterpret_cast<const float4*>(b)[i];
         reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
+__global__ void add_f16_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                               __half* __restrict__ out, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i];
+        const float4 y = reinterpret_cast<const float4*>(b)[i];
+        uint2 u;
+        *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(x.x + y.x, x.y + y.y);
+        *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(x.z + y.z, x.w + y.w);
+        reinterpret_cast<uint2*>(out)[i] = u;
     }
 }
 
@@ -231,33 +250,43 @@ int launch_gemm_f32(const float* A, int lda, const float* Wt, int M, int N, int 
     return ok() ? 1 : -1;
 }
 
-int launch_layernorm(const float* x, const LNW& ln, int rows, int d, float* out, cudaStream_t s) {
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ln.g, ln.b, rows, d, out);
+int launch_layernorm(const float* x, const LNW& ln, int rows, int d, float* out, __half* out16,
+                     cudaStream_t s) {
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ln.g, ln.b, rows, d, out, out16);
     return ok() ? 1 : -1;
 }
 
-int launch_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
-                     int B, int Lq, int Lk, int n_head, int dk, int dv, float* out, int ldo,
+template <class T>
+int launch_attention(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv,
+                     int B, int Lq, int Lk, int n_head, int dk, int dv, T* out, int ldo,
                      cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)Lq * dk + (size_t)Lk * (dk + 1) + (size_t)Lk * dv +
                                          (size_t)Lq * (Lk + 1));
-    if (cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -1;
     dim3 grid(n_head, B);
-    attention_kernel<<<grid, 128, smem, s>>>(q, ldq, k, ldk, v, ldv, Lq, Lk, dk, dv,
+    attention_kernel<T><<<grid, 128, smem, s>>>(q, ldq, k, ldk, v, ldv, Lq, Lk, dk, dv,
                                              1.f / sqrtf((float)dk), out, ldo);
     return ok() ? 1 : -1;
 }
 
-int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F, int P, float* out,
+template int launch_attention<float>(const float*, int, const float*, int, const float*, int, int, int, int, int,
+                                     int, int, float*, int, cudaStream_t);
+template int launch_attention<__half>(const __half*, int, const __half*, int, const __half*, int, int, int, int,
+                                      int, int, int, __half*, int, cudaStream_t);
+
+template <class T>
+int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F, int P, T* out, int ldo,
                       cudaStream_t s) {
     const size_t smem = sizeof(float) * (size_t)(p + F) * (P + 2);
-    if (cudaFuncSetAttribute(prior_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(prior_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -1;
-    prior_conv_kernel<<<B, 256, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,
-                                           w.p_c2w, w.p_c2b, w.p_s2, w.p_t2, out);
+    prior_conv_kernel<T><<<B, 256, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,
+                                              w.p_c2w, w.p_c2b, w.p_s2, w.p_t2, out, ldo);
     return ok() ? 1 : -1;
 }
+template int launch_prior_conv<float>(const Weights&, const float*, int, int, int, int, float*, int, cudaStream_t);
+template int launch_prior_conv<__half>(const Weights&, const float*, int, int, int, int, __half*, int, cudaStream_t);
 
 int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t s) {
     const int64_t n4 = n / 4;   // callers pass multiples of 4 (d_model % 32 == 0)
@@ -266,4 +295,13 @@ int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream
     return ok() ? 1 : -1;
 }
 
+}  // namespace egx
+
+namespace egx {
+int launch_add_f16(const float* a, const float* b, __half* out, int64_t n, cudaStream_t s) {
+    const int64_t n4 = n / 4;
+    const int grid = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 8);
+    add_f16_kernel<<<grid, 256, 0, s>>>(a, b, out, n4);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 }  // namespace egx
