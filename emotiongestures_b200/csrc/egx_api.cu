@@ -558,16 +558,17 @@ int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto,
             const __half* res = x;
             {
                 StageScope sc(h, 3);
-                LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, s));
-                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, s));
+                LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, nullptr, s));
+                // conv2's epilogue also emits the per-tile channel sums the SE gate averages
+                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, sl.se_sums, s));
                 if (bw.has_down) {
-                    LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, sl.down, 0, s));
+                    LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, sl.down, 0, nullptr, s));
                     res = sl.down;
                 }
             }
             StageScope sc(h, 4);
-            LAUNCH(h, launch_se_reduce<__half>(z, B, Ho * Wo, bw.se.c, sl.se_sums, s));
-            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, se_partials(Ho * Wo), B, Ho * Wo, y, s));
+            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, conv_tc_tiles_per_clip(Ho, Wo), B, Ho * Wo, y,
+                                              s));
             std::swap(x, y);
             Hc = Ho; Wc = Wo;
         }
@@ -592,7 +593,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
     if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;
     {
         StageScope sc(h, 3);
-        LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, s));
+        LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, nullptr, s));
     }
     StageScope sc5(h, 5);
     if (linear_tc(h, w.a_fc1, sl.fcin, HW3, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
@@ -918,14 +919,14 @@ int egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const flo
 
 int egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int cin, const void* w16, int cout,
                       int ks, int stride, int relu_first, const float* bias, const float* scale,
-                      const float* shift, void* out16, int nchw, void* stream) {
+                      const float* shift, void* out16, int nchw, float* se_part, void* stream) {
     if (!h || !in16 || !w16 || !scale || !shift || !out16) return 1;
     cudaStream_t s = (cudaStream_t)stream;
     ConvW c;
     c.cin = cin; c.cout = cout; c.ks = ks; c.stride = stride; c.relu_first = relu_first;
     c.w16 = const_cast<__half*>(static_cast<const __half*>(w16));
     c.bias = const_cast<float*>(bias); c.scale = const_cast<float*>(scale); c.shift = const_cast<float*>(shift);
-    LAUNCH(h, launch_conv_tc(c, static_cast<const __half*>(in16), B, H, W, static_cast<__half*>(out16), nchw, s));
+    LAUNCH(h, launch_conv_tc(c, static_cast<const __half*>(in16), B, H, W, static_cast<__half*>(out16), nchw, se_part, s));
     return 0;
 }
 

@@ -196,8 +196,10 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
 
 int conv_tc_init_device();
 // in: NHWC fp16 (B,Hin,Win,cin); out: NHWC fp16 or (B,cout,Ho*Wo) fp16 when nchw != 0
+// se_part (optional): [B][conv_tc_tiles_per_clip(Ho,Wo)][cout] per-tile channel sums (fixed order)
 int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw,
-                   cudaStream_t s);
+                   float* se_part, cudaStream_t s);
+int conv_tc_tiles_per_clip(int Ho, int Wo);
 
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);

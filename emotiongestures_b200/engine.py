@@ -194,7 +194,8 @@ class Engine:
                                                      self._stream()), "egx_debug_linear_tc")
         return out
 
-    def debug_conv_tc(self, x, w, scale, shift, bias=None, stride=1, relu_first=False, nchw=False):
+    def debug_conv_tc(self, x, w, scale, shift, bias=None, stride=1, relu_first=False, nchw=False,
+                      se_sums=False):
         """x (B,Cin,H,W) f32, w (Cout,Cin,ks,ks) f32 -> (B,Cout,Ho,Wo) f32 via the tcgen05 conv kernel."""
         dev = self.device
         b, cin, hh, ww = x.shape
@@ -207,12 +208,18 @@ class Engine:
         out = torch.full(shape, float("nan"), dtype=torch.float16, device=dev)
         bias = None if bias is None else self._f32(bias, "bias")
         scale, shift = self._f32(scale, "scale"), self._f32(shift, "shift")
+        part = torch.full((b * 256 * cout,), float("nan"), device=dev) if se_sums else None
         with torch.cuda.device(dev):
             self._check(self.lib.egx_debug_conv_tc(
                 self._h, _ptr(x16), b, hh, ww, cin, _ptr(w16), cout, ks, stride, int(relu_first), _ptr(bias),
-                _ptr(scale), _ptr(shift), _ptr(out), int(nchw), self._stream()), "egx_debug_conv_tc")
+                _ptr(scale), _ptr(shift), _ptr(out), int(nchw), _ptr(part), self._stream()), "egx_debug_conv_tc")
         out = out.float()
-        return out.view(b, cout, ho, wo) if nchw else out.permute(0, 3, 1, 2).contiguous()
+        out = out.view(b, cout, ho, wo) if nchw else out.permute(0, 3, 1, 2).contiguous()
+        if se_sums:
+            torch.cuda.synchronize()
+            n_used = int((~torch.isnan(part)).sum().item())       # slots are [B][tiles_per_clip][cout]
+            return out, part[:n_used].view(b, -1, cout).sum(dim=1)
+        return out
 
     def fgd_accumulate(self, feats, acc, shift=None):
         """Add the sufficient statistics of feats (n,D) f32 into acc [1+D+D*D] f64."""

@@ -120,11 +120,11 @@ EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, 
 
 /* Parity probe of the tcgen05 implicit-GEMM convolution alone.  in16: NHWC fp16 (B,H,W,cin); w16: fp16
  * [cout][ks*ks][cin]; y = (relu_first ? relu(acc+bias) : acc+bias)*scale + shift; out16: NHWC fp16, or
- * (B,cout,Ho*Wo) fp16 when nchw != 0. */
+ * (B,cout,Ho*Wo) fp16 when nchw != 0; se_part (nullable): [B][tiles][cout] per-tile channel sums. */
 EGX_API int  egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int cin,
                        const void* w16, int cout, int ks, int stride, int relu_first,
                        const float* bias, const float* scale, const float* shift, void* out16,
-                       int nchw, void* stream);
+                       int nchw, float* se_part, void* stream);
 
 /* Measurement hooks (bench.py): with profiling enabled (max_launches > 0) every kernel launch is
  * bracketed by a CUDA-event pair on the launching stream, tagged with its stage of SURVEY.md

@@ -61,3 +61,22 @@ def test_conv_tc(eng, cin, cout, h, w, ks, stride, nchw):
     # output is stored as fp16: half an ulp of the output scale on top of accumulation order
     assert rel_max(got, ref) <= 1.5e-3
     assert ((got - ref).abs() <= 1e-3 * ref.abs() + 2e-3).all()
+
+
+@pytest.mark.parametrize("c,h,w", [(32, 128, 70), (64, 64, 35), (128, 32, 18), (64, 64, 62)])
+def test_conv_tc_se_partial_sums(eng, c, h, w):
+    """conv2's epilogue also emits per-tile channel sums (the SE squeeze); they must add up to the
+    channel sums of the fp32 conv+BN output (not of its fp16 rounding)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(c + h)
+    b = 5
+    x = torch.randn(b, c, h, w, generator=g)
+    wt = torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5
+    scale = torch.rand(c, generator=g) + 0.5
+    shift = torch.randn(c, generator=g) * 0.1
+    got, sums = eng.debug_conv_tc(x, wt, scale, shift, se_sums=True)
+    ref = F.conv2d(x.half().double(), wt.half().double(), padding=1) * scale.double().view(1, -1, 1, 1) \
+        + shift.double().view(1, -1, 1, 1)
+    assert rel_max(got.cpu(), ref) <= 1.5e-3
+    mean_err = (sums.cpu().double() / (h * w) - ref.mean(dim=(2, 3))).abs().max().item()
+    assert mean_err <= 2e-6 * max(1.0, ref.abs().max().item())
