@@ -40,22 +40,32 @@ def finalize_stats(acc, dim: int, shift=None):
     return m, sigma
 
 
+def _trace_sqrt_product(sigma1, sigma2):
+    """Tr sqrt(S1 S2) through the symmetric form sqrt(S1) S2 sqrt(S1): same spectrum as S1 S2, but
+    real-symmetric, so no complex square root is ever formed.  Returns (trace, min eigenvalue)."""
+    w, v = np.linalg.eigh(sigma1)
+    root = (v * np.sqrt(np.clip(w, 0.0, None))) @ v.T
+    lam = np.linalg.eigvalsh(root @ sigma2 @ root)
+    return np.sqrt(np.clip(lam, 0.0, None)).sum(), lam.min()
+
+
 def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
-    """model/FHD_score.py:159-217 (host tail), including its failure conventions: eps*I retry
-    when the product is near-singular, imaginary-part check, and `return 100` on ValueError."""
-    from scipy import linalg
-    mu1, mu2 = np.atleast_1d(mu1), np.atleast_1d(mu2)
-    sigma1, sigma2 = np.atleast_2d(sigma1), np.atleast_2d(sigma2)
-    diff = mu1 - mu2
-    try:
-        covmean, _ = linalg.sqrtm(sigma1.dot(sigma2), disp=False)
-        if not np.isfinite(covmean).all():
-            offset = np.eye(sigma1.shape[0]) * eps
-            covmean = linalg.sqrtm((sigma1 + offset).dot(sigma2 + offset))
-        if np.iscomplexobj(covmean):
-            if not np.allclose(np.diagonal(covmean).imag, 0, atol=1e-3):
-                raise ValueError("Imaginary component {}".format(np.max(np.abs(covmean.imag))))
-            covmean = covmean.real
-    except ValueError:
+    """||mu1-mu2||^2 + Tr S1 + Tr S2 - 2 Tr sqrt(S1 S2)  (model/FHD_score.py:159-217; host tail).
+
+    The reference calls scipy.linalg.sqrtm(..., disp=False), which current scipy no longer accepts;
+    this keeps its observable conventions instead: a non-finite result is retried once with eps*I
+    added to both covariances (:198-203), and a product whose square root would carry an imaginary
+    part above 1e-3 (eigenvalue below -1e-6) returns the sentinel 100 (:206-214)."""
+    mu1, mu2 = np.atleast_1d(np.asarray(mu1, np.float64)), np.atleast_1d(np.asarray(mu2, np.float64))
+    sigma1 = np.atleast_2d(np.asarray(sigma1, np.float64))
+    sigma2 = np.atleast_2d(np.asarray(sigma2, np.float64))
+    if mu1.shape != mu2.shape or sigma1.shape != sigma2.shape:
+        raise AssertionError("mean vectors / covariances have different shapes")
+    tr, lam_min = _trace_sqrt_product(sigma1, sigma2)
+    if not np.isfinite(tr):
+        offset = np.eye(sigma1.shape[0]) * eps
+        tr, lam_min = _trace_sqrt_product(sigma1 + offset, sigma2 + offset)
+    if not np.isfinite(tr) or lam_min < -1e-6:
         return 100
-    return diff.dot(diff) + np.trace(sigma1) + np.trace(sigma2) - 2 * np.trace(covmean)
+    d = mu1 - mu2
+    return float(d @ d + np.trace(sigma1) + np.trace(sigma2) - 2.0 * tr)

@@ -1,0 +1,44 @@
+"""Clip sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+Every clip is independent in eval mode (BatchNorm uses running statistics; InstanceNorm, SE,
+LayerNorm and attention are per clip), so the forward needs no collective.  Communication is
+exactly the two steps BASELINE.json's north star names: the final pose gather and the FGD
+sufficient-statistics all-reduce (fgd.all_reduce_stats).  This replaces the reference's
+single-process nn.DataParallel scatter/replicate/gather per call
+(test_emotion_gesture_diversity_iterative.py:137-138).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_clips: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of the global batch owned by `rank` (sizes differ by <= 1)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, rem = divmod(n_clips, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_poses(local: torch.Tensor, n_clips: int, group=None) -> torch.Tensor:
+    """Gather per-rank pose slices (b_r, F, P) into the global (n_clips, F, P) on every rank.
+    Shards may be ragged (n_clips not divisible by the world size): slices are padded to the
+    largest shard for the collective and trimmed afterwards."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        assert local.shape[0] == n_clips
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_bounds(n_clips, r, world) for r in range(world)]
+    assert local.shape[0] == sizes[rank][1] - sizes[rank][0], "local shard has the wrong size"
+    biggest = max(hi - lo for lo, hi in sizes)
+    send = local
+    if local.shape[0] < biggest:
+        pad = torch.zeros((biggest - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        send = torch.cat([local, pad], dim=0)
+    out = torch.empty((world * biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, send.contiguous(), group=group)
+    parts = [out[r * biggest: r * biggest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,77 @@
+"""CPU: host-side mirror of the reference interface (constructor, state_dict, text encoder,
+error behaviour), geometry helpers and sharding arithmetic."""
+import pytest
+import torch
+
+from emotiongestures_b200 import (BEAT, TED, GeneratorConfig, Transformer, audio_length,
+                                  randomize_norm_stats_, spectrogram_length)
+from emotiongestures_b200.sharding import shard_bounds
+from tests.helpers import model_and_sd
+
+
+def test_geometry_matches_reference_formulas():
+    # utils/data_utils.py:42-44 and lmdb_data_loader_expressive.py:95
+    assert spectrogram_length(34, 15) == 70 and spectrogram_length(60, 15) == 124
+    assert audio_length(34, 15) == 36267 and audio_length(60, 15) == 64000
+    assert TED.trunk_hw == (32, 18) and BEAT.trunk_hw == (32, 31)
+    assert TED.n_stft_frames == 71 and BEAT.n_stft_frames == 126
+    with pytest.raises(ValueError):
+        GeneratorConfig(spec_w=80).validate()
+    with pytest.raises(ValueError):
+        GeneratorConfig(frames=61).validate()
+
+
+def test_constructor_signature_is_the_reference_one():
+    class Args:
+        freeze_wordembed = False; hidden_size = 300; n_layers = 3; wordembed_dim = 300; dropout_prob = 0.1
+
+    class Lang:
+        n_words = 50; word_embedding_weights = None
+
+    # positional order of Full_model/Models.py:298-301
+    g = Transformer(Args(), Lang(), 34, 126, 4, 1, 1, 256, 256, 1024, 3, 8, 64, 64, 0.1, 60, spec_w=70)
+    assert g.cfg.frames == 34 and g.cfg.fc1_in == 576 and g.text_encoder.embedding.num_embeddings == 50
+    with pytest.raises(AssertionError):
+        Transformer(Args(), Lang(), d_word_vec=64, d_model=128)
+
+
+def test_state_dict_roundtrip_and_init():
+    m, sd = model_and_sd("ted", 0)
+    m2 = Transformer.from_config(TED)
+    missing = m2.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # Full_model/Models.py:381-383: xavier_uniform over every parameter with dim > 1
+    torch.manual_seed(0)
+    fresh = Transformer.from_config(TED)
+    w = fresh.audio_encoder.feat_extractor.layer1[0].conv1.weight
+    bound = (6.0 / (32 * 9 + 32 * 9)) ** 0.5
+    assert w.abs().max() <= bound + 1e-6 and w.abs().max() > 0.8 * bound
+    randomize_norm_stats_(fresh, 1)
+    assert (fresh.audio_encoder.bn1.running_var != 1).all()
+
+
+def test_text_encoder_runs_on_cpu_and_is_causal():
+    m, _ = model_and_sd("ted", 0)
+    t = torch.randint(0, 100, (2, 60))
+    with torch.no_grad():
+        out = m.text_encoder(t)
+    assert out.shape == (2, 60, 512)
+
+
+def test_training_mode_is_rejected():
+    m = Transformer.from_config(TED)
+    with pytest.raises(RuntimeError, match="inference path"):
+        m.train()(torch.zeros(1, 128, 70), torch.zeros(1, 60, dtype=torch.int64), torch.zeros(1, 4, 126))
+
+
+def test_shard_bounds_partition_the_batch():
+    for n, world in ((4096, 8), (10, 4), (3, 8), (0, 2), (7, 1)):
+        spans = [shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(8, 2, 2)

@@ -1,0 +1,55 @@
+"""CPU: the float64 log-mel oracle against independent constructions (torchaudio filterbank,
+torch.stft, the reference's own PreEmphasis module arithmetic)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import logmel as ol
+from oracle import synth
+
+
+def test_mel_filterbank_matches_torchaudio_slaney():
+    import torchaudio
+    ta = torchaudio.functional.melscale_fbanks(513, 0.0, 8000.0, 128, 16000, norm="slaney",
+                                               mel_scale="slaney").double().numpy().T
+    fb = ol.mel_filterbank()
+    assert fb.shape == (128, 513)
+    assert np.abs(fb - ta).max() < 1e-6
+    assert (fb >= 0).all() and ((fb > 0).sum(axis=1) >= 1).all()
+
+
+def test_preemphasis_is_the_reference_conv():
+    """model/utils.py:33-38: reflect-pad 1 on the left, cross-correlate with [-0.97, 1]."""
+    x = torch.from_numpy(synth.synth_audio(3, 1000, seed=2)).double()
+    ref = F.conv1d(F.pad(x.unsqueeze(1), (1, 0), "reflect"),
+                   torch.tensor([[[-0.97, 1.0]]], dtype=torch.float64)).squeeze(1)
+    assert np.allclose(ol.preemphasis(x.numpy()), ref.numpy(), atol=1e-15)
+
+
+def test_stft_power_matches_torch_stft():
+    x = synth.synth_audio(2, 36267, seed=4).astype(np.float64)
+    for mode in ("constant", "reflect"):
+        s = torch.stft(torch.from_numpy(x), 1024, 512, window=torch.hann_window(1024, periodic=True, dtype=torch.float64),
+                       center=True, pad_mode=mode, return_complex=True)
+        ref = (s.real ** 2 + s.imag ** 2).numpy()
+        got = ol.stft_power(x, None, mode)
+        assert got.shape == ref.shape == (2, 513, 71)
+        assert np.abs(got - ref).max() < 1e-10 * ref.max()
+
+
+def test_modes_and_shapes():
+    a = synth.synth_audio(2, 36267, seed=1)
+    li = ol.logmel(a, 70, "log_in")
+    assert li.shape == (2, 128, 70)
+    assert np.abs(li.mean(axis=2)).max() < 1e-9 and np.abs(li.var(axis=2) - 1).max() < 1e-3
+    db = ol.logmel(a, 70, "db", preemph=False)
+    assert db.max() == 0.0 and db.min() >= -80.0
+    silent = ol.logmel(np.zeros((1, 36267), np.float32), 70, "db")
+    assert np.all(silent == 0.0)            # amin clamp: everything sits at the reference level
+
+
+def test_fixed_length_audio():
+    a = np.arange(10.0)
+    assert np.array_equal(ol.make_audio_fixed_length(a, 6), a[:6])
+    padded = ol.make_audio_fixed_length(a, 13)
+    assert len(padded) == 13 and np.array_equal(padded[10:], a[::-1][:3])
