@@ -4,11 +4,12 @@
 //   stores fp32 and/or fp16 (the fp16 copy is the A operand of the next GEMM).
 // Follows Full_model/SubLayers.py:39-57,78-82 and Full_model/Models.py:124-130,411-425.
 //
-// One 128 x BN output tile per CTA.  Warp 0: TMA producer (SWIZZLE_128B boxes of 64 fp16 = 128 B rows),
-// warp 1: TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5: epilogue (tcgen05.ld, one accumulator
-// row per thread).  kStages-deep smem ring with full/empty mbarriers; K tails and M/N tails come from TMA
-// zero fill.  Two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's epilogue overlaps the
-// other's MMA stream.
+// Persistent, warp-specialised (same skeleton as k_conv_tc.cu): grid = #SMs, tiles of 128 x BN
+// (BN = 256 when N allows, else 128) walked n-fastest so CTAs running side by side share the A tile in L2.
+//   warp 0    TMA producer (SWIZZLE_128B boxes of 64 fp16 = 128 B rows), runs ahead across tiles
+//   warp 1    single-thread tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2-9 two epilogue groups (even / odd tiles), one accumulator row per thread
+// K tails and M/N tails come from TMA zero fill; stores are predicated.
 #include "egx_common.cuh"
 #include "tc_common.cuh"
 
@@ -20,16 +21,19 @@ using namespace tc;
 
 constexpr int GM = 128;          // tile rows (UMMA M)
 constexpr int GK = 64;           // fp16 elements per K block = one 128-byte swizzle row
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kMaxBias = 2048;   // widest N staged in shared memory
 
 template <int BN>
-struct GemmSmem {
+struct GemmCfg {
     static constexpr int kABytes = GM * GK * 2;
     static constexpr int kBBytes = BN * GK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = BN == 256 ? 4 : 6;
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 128 + 1024;   // barriers + alignment slack
+    static constexpr int kBiasOffset = kBarOffset + 256;
+    static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 1024;
+    static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
 struct GemmTcEpi {
@@ -42,29 +46,33 @@ struct GemmTcEpi {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, GemmTcEpi ep) {
-    using S = GemmSmem<BN>;
+    using S = GemmCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
-    uint64_t* empty = full + kStages;
-    uint64_t* tmem_full = empty + kStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* empty = full + S::kStages;
+    uint64_t* tmem_full = empty + S::kStages;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * GM, n0 = blockIdx.y * BN;
     const int num_kb = (K + GK - 1) / GK;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = ((M + GM - 1) / GM) * n_tiles;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < S::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_ptr);
+    if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_ptr);
+    for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads) sbias[i] = (ep.bias && i < N) ? ep.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -72,94 +80,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int st = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&empty[st], ph ^ 1);
-                unsigned char* a = smem + st * S::kStageBytes;
-                mbar_expect_tx(&full[st], S::kStageBytes);
-                tma_load_2d(a, &tmA, &full[st], kb * GK, m0);
-                tma_load_2d(a + S::kABytes, &tmB, &full[st], kb * GK, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int st = it % S::kStages;
+                    mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
+                    unsigned char* a = smem + st * S::kStageBytes;
+                    mbar_expect_tx(&full[st], S::kStageBytes);
+                    tma_load_2d(a, &tmA, &full[st], kb * GK, m0);
+                    tma_load_2d(a + S::kABytes, &tmB, &full[st], kb * GK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int st = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&full[st], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t a = smem_u32(smem + st * S::kStageBytes);
-                const uint32_t b = a + S::kABytes;
+                const uint32_t d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int st = it % S::kStages;
+                    mbar_wait(&full[st], (it / S::kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(smem + st * S::kStageBytes);
+                    const uint32_t b = a + S::kABytes;
 #pragma unroll
-                for (int k = 0; k < GK / 16; ++k)
-                    umma_f16(tmem_base, make_smem_desc<128>(a + k * 32), make_smem_desc<128>(b + k * 32), idesc,
-                             (kb | k) != 0);
-                umma_commit(&empty[st]);
+                    for (int k = 0; k < GK / 16; ++k)
+                        umma_f16(d, make_smem_desc<128>(a + k * 32), make_smem_desc<128>(b + k * 32), idesc,
+                                 (kb | k) != 0);
+                    umma_commit(&empty[st]);
+                }
+                umma_commit(&tmem_full[acc]);
             }
-            umma_commit(tmem_full);
         }
     } else {
-        // epilogue: warp w owns TMEM lanes [32*(w%4), +32)
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int m = m0 + row;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const float* add_row = nullptr;
-        if (ep.addend && m < M) add_row = ep.addend + (size_t)(ep.addend_rows ? m % ep.addend_rows : m) * ep.addend_ld;
+        const bool relu = ep.relu != 0;
+        const bool add_vec = (ep.addend_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.addend) & 15) == 0;
+        uint32_t tcount = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, tcount += 2) {
+            const int m = (tile / n_tiles) * GM + row, n0 = (tile % n_tiles) * BN;
+            mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
+            tc_fence_after();
+            const float* add_row = nullptr;
+            if (ep.addend && m < M)
+                add_row = ep.addend + (size_t)(ep.addend_rows ? m % ep.addend_rows : m) * ep.addend_ld;
+            const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            float v[32];
-            __syncwarp();
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-            const int nb = n0 + c * 32;
-            if (m < M && nb < N) {
+            for (int c = 0; c < BN / 32; ++c) {
+                const int nb = n0 + c * 32;
+                if (nb >= N) break;                       // warp-uniform
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                if (m < M) {
+                    const bool full_chunk = nb + 32 <= N;
+                    if (full_chunk) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                float t = v[j];
-                if (n < N) {
-                    if (ep.bias) t += __ldg(ep.bias + n);
-                    if (ep.relu) t = fmaxf(t, 0.f);
-                    if (add_row) t += __ldg(add_row + n);
-                }
-                v[j] = t;
-            }
-            const bool full_chunk = nb + 32 <= N;
-            if (ep.out32) {
-                float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
-                if (full_chunk && (ep.ld32 & 3) == 0) {
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bi = *reinterpret_cast<const float4*>(sbias + nb + 4 * j4);
+                            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (add_row) {
+                                if (add_vec) ad = __ldg(reinterpret_cast<const float4*>(add_row + nb) + j4);
+                                else ad = make_float4(__ldg(add_row + nb + 4 * j4), __ldg(add_row + nb + 4 * j4 + 1),
+                                                      __ldg(add_row + nb + 4 * j4 + 2), __ldg(add_row + nb + 4 * j4 + 3));
+                            }
+                            const float bv[4] = {bi.x, bi.y, bi.z, bi.w}, av[4] = {ad.x, ad.y, ad.z, ad.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && nb + j < N; ++j) o[j] = v[j];
-                }
-            }
-            if (ep.out16) {
-                __half* o = ep.out16 + (size_t)m * ep.ld16 + nb;
-                if (full_chunk && (ep.ld16 & 7) == 0) {
+                            for (int e = 0; e < 4; ++e) {
+                                float t = v[4 * j4 + e] + bv[e];
+                                if (relu) t = fmaxf(t, 0.f);
+                                v[4 * j4 + e] = t + av[e];
+                            }
+                        }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-                        *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                        *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                        *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                        reinterpret_cast<uint4*>(o)[j] = u;
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            float t = v[j];
+                            if (n < N) {
+                                t += sbias[n];
+                                if (relu) t = fmaxf(t, 0.f);
+                                if (add_row) t += __ldg(add_row + n);
+                            }
+                            v[j] = t;
+                        }
                     }
-                } else {
-                    for (int j = 0; j < 32 && nb + j < N; ++j) o[j] = __float2half_rn(v[j]);
+                    if (ep.out32) {
+                        float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
+                        if (full_chunk && (ep.ld32 & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<float4*>(o)[j] =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < N) o[j] = v[j];
+                        }
+                    }
+                    if (ep.out16) {
+                        __half* o = ep.out16 + (size_t)m * ep.ld16 + nb;
+                        if (full_chunk && (ep.ld16 & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+                                *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+                                *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+                                *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+                                reinterpret_cast<uint4*>(o)[j] = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < N) o[j] = __float2half_rn(v[j]);
+                        }
+                    }
                 }
             }
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[grp]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<BN>(tmem_base);
+    if (warp == 1) tmem_dealloc<S::kTmemCols>(tmem_base);
 }
 
 __global__ void cvt_pad_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in,
@@ -172,12 +225,35 @@ __global__ void cvt_pad_kernel(const float* __restrict__ in, int64_t rows, int c
     }
 }
 
+int g_gemm_sms = 0;
+
+template <int BN>
+int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmTcEpi& ep,
+              cudaStream_t s) {
+    CUtensorMap ta, tb;
+    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, dB[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t sA[1] = {(uint64_t)lda * 2}, sB[1] = {(uint64_t)ldw * 2};
+    const uint32_t bA[2] = {GK, GM}, bB[2] = {GK, BN};
+    if (!make_tmap_f16(&ta, A, 2, dA, sA, bA, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (!make_tmap_f16(&tb, W, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
+    const int grid = tiles < g_gemm_sms ? tiles : g_gemm_sms;
+    gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmCfg<BN>::kTotal, s>>>(ta, tb, M, N, K, ep);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 }  // namespace
 
 // per-device one-time setup (opt-in shared memory size)
 int gemm_tc_init_device() {
-    return cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<128>::kTotal) == cudaSuccess ? 0 : -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<128>::kTotal) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<256>::kTotal) != cudaSuccess) return -1;
+    return 0;
 }
 
 // fp32 [rows][cols] (pitch ld_in) -> fp16 [rows][ld_out], columns >= cols zeroed
@@ -191,17 +267,10 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 // A: [M][K] fp16 with row pitch lda (elements, multiple of 8); W: [N][K] fp16 with row pitch ldw.
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
-    constexpr int BN = 128;
-    CUtensorMap ta, tb;
-    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, dB[2] = {(uint64_t)K, (uint64_t)N};
-    const uint64_t sA[1] = {(uint64_t)lda * 2}, sB[1] = {(uint64_t)ldw * 2};
-    const uint32_t bA[2] = {GK, GM}, bB[2] = {GK, BN};
-    if (!make_tmap_f16(&ta, A, 2, dA, sA, bA, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    if (!make_tmap_f16(&tb, W, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (N > kMaxBias) return -1;
     GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16};
-    dim3 grid((M + GM - 1) / GM, (N + BN - 1) / BN);
-    gemm_tc_kernel<BN><<<grid, kThreads, GemmSmem<BN>::kTotal, s>>>(ta, tb, M, N, K, ep);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    if (N % 256 == 0) return launch_bn<256>(A, lda, W, ldw, M, N, K, ep, s);
+    return launch_bn<128>(A, lda, W, ldw, M, N, K, ep, s);
 }
 
 }  // namespace egx
