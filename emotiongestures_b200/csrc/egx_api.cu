@@ -620,8 +620,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         const FFNW& f = w.enc_ffn[l];
         const bool last = l == c.n_layers - 1;
         if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
-        LAUNCH(h, launch_attention<__half>(sl.qkv16, 3 * hk, sl.qkv16 + hk, 3 * hk, sl.qkv16 + 2 * hk, 3 * hk, B, F, F,
-                                           c.n_head, c.d_k, c.d_v, sl.o16, hk, s));
+        LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, F, c.n_head, sl.o16, hk, s));
         if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, x32, 0, s)) return 1;
         LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
@@ -637,8 +636,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         __half* kv = sl.qkv16 + (size_t)R * hk;
         if (linear_tc(h, a.q, dx16, d, R, nullptr, 0, sl.qkv16, hk, 0, nullptr, 0, s)) return 1;
         if (linear_tc(h, a.kv, sl.enc16, d, R, nullptr, 0, kv, 2 * hk, 0, nullptr, 0, s)) return 1;
-        LAUNCH(h, launch_attention<__half>(sl.qkv16, hk, kv, 2 * hk, kv + hk, 2 * hk, B, F, F, c.n_head, c.d_k, c.d_v,
-                                           sl.o16, hk, s));
+        LAUNCH(h, launch_attention_tc(sl.qkv16, hk, 0, kv, 2 * hk, 0, hk, B, F, c.n_head, sl.o16, hk, s));
         if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, dx32, 0, s)) return 1;
         LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
@@ -722,7 +720,11 @@ int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
     h->H[0] = c.n_mels; h->W[0] = c.spec_w;
     for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
     if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
-    if (gemm_tc_init_device() != 0 || conv_tc_init_device() != 0) { egx_destroy(h); return 6; }
+    if (gemm_tc_init_device() != 0 || conv_tc_init_device() != 0 || attn_tc_init_device() != 0) {
+        egx_destroy(h);
+        return 6;
+    }
+    if (c.precision == EGX_PREC_TC && (c.d_k != 64 || c.d_v != 64)) { egx_destroy(h); return 4; }
     *out = h;
     return 0;
 }
@@ -927,6 +929,15 @@ int egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int 
     c.w16 = const_cast<__half*>(static_cast<const __half*>(w16));
     c.bias = const_cast<float*>(bias); c.scale = const_cast<float*>(scale); c.shift = const_cast<float*>(shift);
     LAUNCH(h, launch_conv_tc(c, static_cast<const __half*>(in16), B, H, W, static_cast<__half*>(out16), nchw, se_part, s));
+    return 0;
+}
+
+int egx_debug_attention_tc(egx_handle* h, const void* q16, int ldq, int q_col0, const void* kv16, int ldkv, int k_col0,
+                           int v_col0, int B, int L, int n_head, void* out16, int ldo, void* stream) {
+    if (!h || !q16 || !kv16 || !out16) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_attention_tc(static_cast<const __half*>(q16), ldq, q_col0, static_cast<const __half*>(kv16), ldkv,
+                                  k_col0, v_col0, B, L, n_head, static_cast<__half*>(out16), ldo, s));
     return 0;
 }
 

@@ -201,6 +201,12 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
                    float* se_part, cudaStream_t s);
 int conv_tc_tiles_per_clip(int Ho, int Wo);
 
+int attn_tc_init_device();
+// softmax((q/8) k^T) v per (clip, head) on tcgen05; d_k = d_v = 64.  Head h of q at columns q_col0 + 64 h of
+// rows (B*L, ldq); k / v at k_col0 / v_col0 + 64 h of rows (B*L, ldkv); out (B*L, ldo), head h at 64 h.
+int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, int ldkv, int k_col0, int v_col0,
+                        int B, int L, int n_head, __half* out, int ldo, cudaStream_t s);
+
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);
 

@@ -221,6 +221,20 @@ class Engine:
             return out, part[:n_used].view(b, -1, cout).sum(dim=1)
         return out
 
+    def debug_attention_tc(self, q, k, v):
+        """q (B,H,Lq,64), k/v (B,H,L,64) f32 -> (B,H,L,64) f32 through the tcgen05 attention kernel,
+        using the packed [rows][3*H*64] layout the QKV GEMM produces."""
+        b, nh, ll, dk = q.shape
+        qkv = torch.cat([t.permute(0, 2, 1, 3).reshape(b * ll, nh * dk) for t in (q, k, v)], dim=1)
+        qkv = qkv.to(self.device).half().contiguous()
+        out = torch.full((b * ll, nh * dk), float("nan"), dtype=torch.float16, device=self.device)
+        hk = nh * dk
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_debug_attention_tc(self._h, _ptr(qkv), 3 * hk, 0, _ptr(qkv), 3 * hk, hk, 2 * hk,
+                                                        b, ll, nh, _ptr(out), hk, self._stream()),
+                        "egx_debug_attention_tc")
+        return out.float().view(b, ll, nh, dk).permute(0, 2, 1, 3).contiguous()
+
     def fgd_accumulate(self, feats, acc, shift=None):
         """Add the sufficient statistics of feats (n,D) f32 into acc [1+D+D*D] f64."""
         f = self._f32(feats, "feats")

@@ -126,6 +126,12 @@ EGX_API int  egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, in
                        const float* bias, const float* scale, const float* shift, void* out16,
                        int nchw, float* se_part, void* stream);
 
+/* Parity probe of the tcgen05 attention kernel alone (fp16 in/out, d_k = d_v = 64): head h of q at columns
+ * q_col0 + 64 h of rows (B*L, ldq); k / v at k_col0 / v_col0 + 64 h of rows (B*L, ldkv). */
+EGX_API int  egx_debug_attention_tc(egx_handle* h, const void* q16, int ldq, int q_col0, const void* kv16,
+                            int ldkv, int k_col0, int v_col0, int B, int L, int n_head, void* out16,
+                            int ldo, void* stream);
+
 /* Measurement hooks (bench.py): with profiling enabled (max_launches > 0) every kernel launch is
  * bracketed by a CUDA-event pair on the launching stream, tagged with its stage of SURVEY.md
  * §8(d) (1 front-end, 2 stem, 3 trunk convolutions, 4 SE gate/apply, 5 projection GEMMs,

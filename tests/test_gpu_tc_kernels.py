@@ -80,3 +80,15 @@ def test_conv_tc_se_partial_sums(eng, c, h, w):
     assert rel_max(got.cpu(), ref) <= 1.5e-3
     mean_err = (sums.cpu().double() / (h * w) - ref.mean(dim=(2, 3))).abs().max().item()
     assert mean_err <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("b,l", [(3, 34), (7, 34), (1, 34), (4, 60), (5, 60), (2, 17), (130, 34)])
+def test_attention_tc(eng, b, l):
+    """Clip packing (3 x 34 / 2 x 60 rows per tile), ragged last group, block-diagonal masking."""
+    g = torch.Generator().manual_seed(b * 100 + l)
+    q, k, v = (torch.randn(b, 8, l, 64, generator=g) * s for s in (1.5, 1.5, 1.0))
+    got = eng.debug_attention_tc(q, k, v).cpu()
+    qd, kd, vd = q.half().double(), k.half().double(), v.half().double()
+    ref = torch.softmax((qd / 8.0) @ kd.transpose(2, 3), dim=-1) @ vd
+    assert not torch.isnan(got).any()
+    assert rel_max(got, ref) <= 2e-3          # fp16 P and fp16 output
