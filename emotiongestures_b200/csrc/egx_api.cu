@@ -567,7 +567,7 @@ int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto,
                 }
             }
             StageScope sc(h, 4);
-            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, conv_tc_tiles_per_clip(Ho, Wo), B, Ho * Wo, y,
+            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, conv_tc_tiles_per_clip(bw.conv2.cin, bw.conv2.cout, Ho, Wo), B, Ho * Wo, y,
                                               s));
             std::swap(x, y);
             Hc = Ho; Wc = Wo;

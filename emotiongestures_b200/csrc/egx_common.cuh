@@ -199,7 +199,7 @@ int conv_tc_init_device();
 // se_part (optional): [B][conv_tc_tiles_per_clip(Ho,Wo)][cout] per-tile channel sums (fixed order)
 int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw,
                    float* se_part, cudaStream_t s);
-int conv_tc_tiles_per_clip(int Ho, int Wo);
+int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo);
 
 int attn_tc_init_device();
 // softmax((q/8) k^T) v per (clip, head) on tcgen05; d_k = d_v = 64.  Head h of q at columns q_col0 + 64 h of

@@ -2,7 +2,10 @@
 // Full_model/SubLayers.py:43-52): softmax((q / sqrt(d_k)) k^T) v per (clip, head), mask None.
 //
 // The sequences are 34 (TED) or 60 (BEAT) tokens, far below a 128-row MMA tile, so G = floor(128 / L) clips
-// are packed into one tile (3 x 34 = 102 rows, 2 x 60 = 120 rows) and the score matrix is block diagonal:
+// are packed into one tile (3 x 34 = 102 rows, 2 x 60 = 120 rows) and the score matrix is block diagonal.
+// Each clip's keys start at a multiple of 16 columns (LP = L rounded up to 16; 48 / 64), so every clip sees
+// the same K-step boundaries in the second MMA whatever its slot in the group: a clip's result is
+// bit-identical for any batch size, sharding or GPU count.
 //   S[128 x NK] = Q_tile[128 x 64] K_tile[NK x 64]^T        (UMMA, both operands K-major)
 //   softmax over the L columns of the row's own clip, other columns written as exact zeros
 //   O[128 x 64] = P[128 x NK] V_tile[NK x 64]               (UMMA, A = P K-major from smem, B = V MN-major)
@@ -24,12 +27,14 @@ namespace {
 using namespace tc;
 
 constexpr int kAttnThreads = 192;
-constexpr int kTileBytes = 128 * 128;                 // 128 rows x 64 fp16
-constexpr int kPBytes = 2 * kTileBytes;               // P: up to 128 key columns = two 64-wide swizzle atoms
-constexpr int kAttnSmem = 3 * kTileBytes + kPBytes + 256 + 1024;
+constexpr int kTileBytes = 128 * 128;                 // 128 rows x 64 fp16 (Q tile; one P swizzle atom)
+constexpr int kMaxNK = 144;                           // key columns per tile (G * LP)
+constexpr int kKVBytes = kMaxNK * 128;                // K / V tiles: one 128-byte row per key
+constexpr int kPBytes = 3 * kTileBytes;               // P: up to 192 key columns = three 64-wide swizzle atoms
+constexpr int kAttnSmem = kTileBytes + 2 * kKVBytes + kPBytes + 256 + 1024;
 
 struct AttnParams {
-    int n_clips, L, G, NK;       // tokens per clip, clips per tile, key columns padded to 16
+    int n_clips, L, G, LP, NK;   // tokens per clip, clips per tile, key slots per clip (16-aligned), G * LP
     int n_head, n_groups;
     int q_col0, k_col0, v_col0;  // column of head 0 inside the q / kv source rows
     __half* out; int ldo;
@@ -48,9 +53,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
     unsigned char* sK = smem + kTileBytes;
-    unsigned char* sV = smem + 2 * kTileBytes;
-    unsigned char* sP = smem + 3 * kTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTileBytes + kPBytes);
+    unsigned char* sV = sK + kKVBytes;
+    unsigned char* sP = sV + kKVBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
     uint64_t* full = bars;          // Q/K/V landed
     uint64_t* empty = bars + 1;     // Q/K/V consumed (both MMAs done)
     uint64_t* s_full = bars + 2;    // scores in TMEM
@@ -69,14 +74,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_ptr);
-    // V rows [rows, NK) are never written by TMA but are read by the second MMA: they must be finite (x 0)
-    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
+    // the padding key rows of V are never written by TMA but are read by the second MMA: they must be finite (x 0)
+    for (int i = threadIdx.x; i < kKVBytes / 16; i += kAttnThreads) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 192;   // S: up to kMaxNK (<= 192) columns, O: 64
 
     if (warp == 0) {
         if (elect_one()) {
@@ -88,8 +93,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_wait(empty, (it & 1) ^ 1);
                 mbar_expect_tx(full, bytes);
                 tma_load_2d(sQ, &tmQ, full, p.q_col0 + h * 64, row0);
-                tma_load_2d(sK, &tmKV, full, p.k_col0 + h * 64, row0);
-                tma_load_2d(sV, &tmKV, full, p.v_col0 + h * 64, row0);
+                for (int cl = 0; cl < p.G; ++cl) {        // one box per clip, landing on its 16-aligned key slot
+                    tma_load_2d(sK + cl * p.LP * 128, &tmKV, full, p.k_col0 + h * 64, row0 + cl * p.L);
+                    tma_load_2d(sV + cl * p.LP * 128, &tmKV, full, p.v_col0 + h * 64, row0 + cl * p.L);
+                }
             }
         }
     } else if (warp == 1) {
@@ -118,7 +125,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const int cl = r / p.L;                       // clip within the group (>= G for unused rows)
-        const int c_lo = cl * p.L, c_hi = c_lo + p.L; // own key columns
+        const int c_lo = cl * p.LP, c_hi = c_lo + p.L; // own key columns
         const bool row_used = r < rows;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         unsigned char* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
@@ -216,7 +223,11 @@ int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, 
                         int L, int n_head, __half* out, int ldo, cudaStream_t s) {
     if (L < 1 || L > 128) return -1;
     AttnParams p;
-    p.n_clips = B; p.L = L; p.G = 128 / L; p.NK = (p.G * L + 15) / 16 * 16;
+    p.n_clips = B; p.L = L; p.LP = (L + 15) / 16 * 16;
+    p.G = 128 / L;
+    while (p.G > 1 && p.G * p.LP > kMaxNK) --p.G;
+    p.NK = p.G * p.LP;
+    if (p.NK > kMaxNK) return -1;
     p.n_head = n_head; p.n_groups = (B + p.G - 1) / p.G;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.out = out; p.ldo = ldo;
@@ -225,9 +236,9 @@ int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, 
     CUtensorMap tq, tkv;
     const uint64_t dq[2] = {(uint64_t)ldq, (uint64_t)B * L}, dkv[2] = {(uint64_t)ldkv, (uint64_t)B * L};
     const uint64_t sq[1] = {(uint64_t)ldq * 2}, skv[1] = {(uint64_t)ldkv * 2};
-    const uint32_t box[2] = {64, (uint32_t)rows};
+    const uint32_t box[2] = {64, (uint32_t)rows}, box_kv[2] = {64, (uint32_t)L};
     if (!make_tmap_f16(&tq, q, 2, dq, sq, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    if (!make_tmap_f16(&tkv, kv, 2, dkv, skv, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (!make_tmap_f16(&tkv, kv, 2, dkv, skv, box_kv, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     const int tiles = p.n_groups * n_head;
     const int grid = tiles < 2 * g_attn_sms ? tiles : 2 * g_attn_sms;
     attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tkv, p);

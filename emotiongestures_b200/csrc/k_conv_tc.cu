@@ -23,6 +23,8 @@
 #include "egx_common.cuh"
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 namespace egx {
 
 namespace {
@@ -34,7 +36,8 @@ constexpr int kSmemBudget = 200 * 1024;
 
 struct ConvTcParams {
     int Ho, Wo;            // output map
-    int BW, BH;            // output patch per tile (BW*BH <= 128)
+    int BW, BH;            // output patch per tile
+    int MW;                // row pitch of the M index: BW, or BW + 2 with halo reuse (MW*BH <= 128)
     int tiles_w, tiles_h;
     int num_tiles;         // B * tiles_h * tiles_w
     int ks, stride, pad;
@@ -48,7 +51,14 @@ struct ConvTcParams {
     float* se_part;        // [B][tiles_h*tiles_w][cout] partial channel sums, or null
 };
 
-template <int CIN, int NPAD, int TAPS>
+// HALO (stride-1 3x3 with resident weights): instead of nine shifted boxes per tile, ONE box per 64-channel
+// chunk brings the (BH+2) x (BW+2) input patch; the M index runs over BH x (BW+2) positions (two junk
+// columns per row), so tap (dy,dx) is the SAME shared-memory patch read from a start address shifted by
+// (dy*(BW+2)+dx) rows.  TMA and UMMA both apply the 128B/64B swizzle on absolute shared-memory address
+// bits, so a row-shifted descriptor still sees the pattern TMA wrote.  L2->SM traffic per tile drops ~7x.
+constexpr int kPatchRows = 176;          // >= 128 + 2*(BW+2) + 2 with BW + 2 <= 20
+
+template <int CIN, int NPAD, int TAPS, bool HALO = false>
 struct ConvCfg {
     static constexpr int CK = CIN < 64 ? CIN : 64;           // channels per K block
     static constexpr int kSwz = CK * 2;                      // 64 or 128 byte rows
@@ -58,8 +68,10 @@ struct ConvCfg {
     static constexpr int kBBytes = ((NPAD * kSwz + 1023) / 1024) * 1024;
     static constexpr bool kResidentB = kNumKb * kBBytes <= 80 * 1024;
     // K blocks handled per pipeline stage (one barrier round-trip): keep >= 4 MMAs of work per wait
-    static constexpr int kKbPerStage = (CK == 32 && TAPS == 9) ? 3 : 1;
-    static constexpr int kStageBytes = kKbPerStage * (kABytes + (kResidentB ? 0 : kBBytes));
+    static constexpr int kKbPerStage = HALO ? kNumKb : ((CK == 32 && TAPS == 9) ? 3 : 1);
+    static constexpr int kPatchBytes = kPatchRows * kSwz;
+    static constexpr int kStageBytes = HALO ? kChunks * kPatchBytes
+                                            : kKbPerStage * (kABytes + (kResidentB ? 0 : kBBytes));
     static constexpr int kResBytes = kResidentB ? kNumKb * kBBytes : 0;
     static constexpr int kStagesRaw = (kSmemBudget - kResBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -72,14 +84,15 @@ struct ConvCfg {
     static constexpr uint32_t kTmemCols = 2 * kAccStride;
     static_assert(kNumKb % kKbPerStage == 0, "stage must divide the K loop");
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
+    static_assert(!HALO || (TAPS == 9 && kResidentB), "halo reuse needs a 3x3 conv with resident weights");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
 
-template <int CIN, int NPAD, int TAPS>
+template <int CIN, int NPAD, int TAPS, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
-    using S = ConvCfg<CIN, NPAD, TAPS>;
+    using S = ConvCfg<CIN, NPAD, TAPS, HALO>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* ring = smem + S::kResBytes;
@@ -131,6 +144,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int t = tile - b * tiles_per_clip;
                 const int wi0 = (t % p.tiles_w) * p.BW * p.stride - p.pad;
                 const int hi0 = (t / p.tiles_w) * p.BH * p.stride - p.pad;
+                if (HALO) {
+                    const int st = it % S::kStages;
+                    mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
+                    unsigned char* dst = ring + st * S::kStageBytes;
+                    mbar_expect_tx(&full[st], (uint32_t)S::kChunks * p.MW * (p.BH + 2) * S::kSwz);
+#pragma unroll
+                    for (int ch = 0; ch < S::kChunks; ++ch)
+                        tma_load_4d(dst + ch * S::kPatchBytes, &tmA, &full[st], ch * S::CK, wi0, hi0, b);
+                    ++it;
+                    continue;
+                }
                 for (int sg = 0; sg < S::kStagesPerTile; ++sg, ++it) {
                     const int st = it % S::kStages;
                     mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
@@ -160,6 +184,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * S::kAccStride;
+                if (HALO) {
+                    const int st = it % S::kStages;
+                    mbar_wait(&full[st], (it / S::kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(ring + st * S::kStageBytes);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)((tap / 3) * p.MW + (tap % 3)) * S::kSwz;
+#pragma unroll
+                        for (int ch = 0; ch < S::kChunks; ++ch) {
+                            const uint32_t a = a0 + ch * S::kPatchBytes + shift;
+                            const uint32_t bb = smem_u32(smem + (tap * S::kChunks + ch) * S::kBBytes);
+#pragma unroll
+                            for (int k = 0; k < S::CK / 16; ++k)
+                                umma_f16(d, make_smem_desc<S::kSwz>(a + k * 32), make_smem_desc<S::kSwz>(bb + k * 32),
+                                         idesc, (tap | ch | k) != 0);
+                        }
+                    }
+                    umma_commit(&empty[st]);
+                    umma_commit(&tmem_full[acc]);
+                    ++it;
+                    continue;
+                }
                 for (int sg = 0; sg < S::kStagesPerTile; ++sg, ++it) {
                     const int st = it % S::kStages;
                     mbar_wait(&full[st], (it / S::kStages) & 1);
@@ -186,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grp = (warp - 2) >> 2;          // accumulator buffer / tile parity this group drains
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;
-        const int ph_ = r / p.BW, pw_ = r % p.BW;
+        const int ph_ = r / p.MW, pw_ = r % p.MW;
         float* red = reinterpret_cast<float*>(smem + S::kRedOffset) + grp * 512;
         const bool relu_first = p.relu_first != 0;
         uint32_t tcount = grp;
@@ -194,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int b = tile / tiles_per_clip;
             const int t = tile - b * tiles_per_clip;
             const int ho = (t / p.tiles_w) * p.BH + ph_, wo = (t % p.tiles_w) * p.BW + pw_;
-            const bool valid = r < p.BW * p.BH && ho < p.Ho && wo < p.Wo;
+            const bool valid = ph_ < p.BH && pw_ < p.BW && ho < p.Ho && wo < p.Wo;
             mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
             tc_fence_after();
             const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
@@ -286,17 +333,32 @@ void pick_patch(int Ho, int Wo, int* bw, int* bh) {
     }
 }
 
-int g_num_sms = 0;
 
-template <int CIN, int NPAD, int TAPS>
+// halo variant: BW + 2 <= 20 and BH * (BW + 2) <= 128; fewest tiles wins
+void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
+    long best = -1;
+    *bw = 1; *bh = 1;
+    for (int w = 1; w <= 18 && w <= Wo; ++w) {
+        const int h = (128 / (w + 2)) < Ho ? (128 / (w + 2)) : Ho;
+        const long tiles = (long)((Ho + h - 1) / h) * ((Wo + w - 1) / w);
+        if (best < 0 || tiles <= best) { best = tiles; *bw = w; *bh = h; }
+    }
+}
+
+int g_num_sms = 0;
+int g_halo = 1;      // EGX_CONV_HALO=0 disables the halo-reuse variant
+
+template <int CIN, int NPAD, int TAPS, bool HALO>
 int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw, float* se_part,
                cudaStream_t s) {
-    using S = ConvCfg<CIN, NPAD, TAPS>;
+    using S = ConvCfg<CIN, NPAD, TAPS, HALO>;
     ConvTcParams p;
     p.ks = c.ks; p.stride = c.stride; p.pad = c.ks / 2;
     p.Ho = (Hin + 2 * p.pad - c.ks) / c.stride + 1;
     p.Wo = (Win + 2 * p.pad - c.ks) / c.stride + 1;
-    pick_patch(p.Ho, p.Wo, &p.BW, &p.BH);
+    if (HALO) pick_halo_patch(p.Ho, p.Wo, &p.BW, &p.BH);
+    else pick_patch(p.Ho, p.Wo, &p.BW, &p.BH);
+    p.MW = HALO ? p.BW + 2 : p.BW;
     p.tiles_w = (p.Wo + p.BW - 1) / p.BW;
     p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
     p.num_tiles = B * p.tiles_w * p.tiles_h;
@@ -308,7 +370,8 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     const uint64_t dA[4] = {(uint64_t)CIN, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     const uint64_t sA[3] = {(uint64_t)CIN * 2, (uint64_t)Win * CIN * 2, (uint64_t)Hin * Win * CIN * 2};
     // with an element (traversal) stride e the box spans boxDim positions and keeps ceil(boxDim / e) of them
-    const uint32_t bA[4] = {(uint32_t)S::CK, (uint32_t)(p.BW * c.stride), (uint32_t)(p.BH * c.stride), 1};
+    const uint32_t bA[4] = {(uint32_t)S::CK, (uint32_t)(HALO ? p.MW : p.BW * c.stride),
+                            (uint32_t)(HALO ? p.BH + 2 : p.BH * c.stride), 1};
     const uint32_t eA[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
     const CUtensorMapSwizzle swz = S::kSwz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if (!make_tmap_f16(&ta, in, 4, dA, sA, bA, eA, swz)) return -1;
@@ -318,14 +381,14 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     const uint32_t bB[2] = {(uint32_t)S::CK, (uint32_t)NPAD};
     if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, swz)) return -1;
     const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-    conv_tc_kernel<CIN, NPAD, TAPS><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, p);
+    conv_tc_kernel<CIN, NPAD, TAPS, HALO><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-template <int CIN, int NPAD, int TAPS>
+template <int CIN, int NPAD, int TAPS, bool HALO = false>
 int set_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<CIN, NPAD, TAPS>::kTotal) == cudaSuccess ? 0 : -1;
+    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<CIN, NPAD, TAPS, HALO>::kTotal) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
@@ -334,15 +397,17 @@ int conv_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (const char* e = getenv("EGX_CONV_HALO")) g_halo = atoi(e);
     return set_attr<32, 32, 9>() | set_attr<32, 64, 9>() | set_attr<64, 64, 9>() | set_attr<64, 128, 9>() |
            set_attr<128, 128, 9>() | set_attr<128, 48, 9>() | set_attr<128, 64, 9>() | set_attr<32, 64, 1>() |
-           set_attr<64, 128, 1>();
+           set_attr<64, 128, 1>() | set_attr<32, 32, 9, true>() | set_attr<64, 64, 9, true>();
 }
 
 // SE partial-sum slots a conv writes per clip (tiles per clip) for an Ho x Wo output map
-int conv_tc_tiles_per_clip(int Ho, int Wo) {
+int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo) {
     int bw, bh;
-    pick_patch(Ho, Wo, &bw, &bh);
+    if (g_halo && cin == cout && (cin == 32 || cin == 64)) pick_halo_patch(Ho, Wo, &bw, &bh);
+    else pick_patch(Ho, Wo, &bw, &bh);
     return ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
 }
 
@@ -352,8 +417,12 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
                    cudaStream_t s) {
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
     if (c.cout > 128 || (!nchw && c.cout % 32)) return -1;
+    if (g_halo && c.ks == 3 && c.stride == 1 && !nchw) {
+        if (c.cin == 32 && c.cout == 32) return launch_one<32, 32, 9, true>(c, in, B, Hin, Win, out, nchw, se_part, s);
+        if (c.cin == 64 && c.cout == 64) return launch_one<64, 64, 9, true>(c, in, B, Hin, Win, out, nchw, se_part, s);
+    }
 #define EGX_CONV_CASE(CI, NP, TP) \
-    if (c.cin == CI && npad == NP && c.ks * c.ks == TP) return launch_one<CI, NP, TP>(c, in, B, Hin, Win, out, nchw, se_part, s);
+    if (c.cin == CI && npad == NP && c.ks * c.ks == TP) return launch_one<CI, NP, TP, false>(c, in, B, Hin, Win, out, nchw, se_part, s);
     EGX_CONV_CASE(32, 32, 9)
     EGX_CONV_CASE(32, 64, 9)
     EGX_CONV_CASE(64, 64, 9)

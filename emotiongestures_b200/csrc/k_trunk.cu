@@ -39,50 +39,58 @@ template <> struct Vec4<__half> {
 };
 
 // ------------------------------------------------------------------------------------------
-// K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  One thread = one pixel x 4 channels; a
-// warp covers 4 consecutive pixels x 32 channels, so stores are fully coalesced and the nine
-// taps of a pixel are shared through L1.
+// K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  grid (row strips, B).  The strip's input rows
+// (+1 halo row each side, zero padded) are staged in shared memory; a thread owns 8 output
+// channels whose 72 weights + bias / BN affine live in registers for the whole strip, so the
+// inner loop is 9 LDS + 72 FMA per 16-byte (8 x fp16) store.  Bandwidth-bound by construction:
+// 4*H*W bytes in, 2*32*H*W bytes out per clip, stores fully coalesced (a warp writes 512
+// contiguous bytes).
 // ------------------------------------------------------------------------------------------
+constexpr int kStemRows = 8;
+
 template <class T>
 __global__ void __launch_bounds__(256)
-stem_kernel(const float* __restrict__ spec, int B, int H, int W, const float* __restrict__ w,
+stem_kernel(const float* __restrict__ spec, int H, int W, const float* __restrict__ w,
             const float* __restrict__ bias, const float* __restrict__ scale,
             const float* __restrict__ shift, T* __restrict__ out) {
-    __shared__ float sw[32 * 9], sb[32], ss[32], st[32];
-    for (int i = threadIdx.x; i < 32 * 9; i += blockDim.x) sw[i] = w[i];
-    if (threadIdx.x < 32) {
-        sb[threadIdx.x] = bias[threadIdx.x];
-        ss[threadIdx.x] = scale[threadIdx.x];
-        st[threadIdx.x] = shift[threadIdx.x];
+    extern __shared__ float s_in[];                       // [(kStemRows + 2)][W + 2]
+    const int PW = W + 2;
+    const int b = blockIdx.y, y0 = blockIdx.x * kStemRows;
+    const float* img = spec + (size_t)b * H * W;
+    for (int i = threadIdx.x; i < (kStemRows + 2) * PW; i += blockDim.x) {
+        const int yy = y0 + i / PW - 1, xx = i % PW - 1;
+        s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[yy * W + xx] : 0.f;
+    }
+    const int cg = threadIdx.x & 3;                        // channels [8*cg, 8*cg + 8)
+    float wr[8][9], br[8], sr[8], tr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wr[j][k] = w[c * 9 + k];
+        br[j] = bias[c]; sr[j] = scale[c]; tr[j] = shift[c];
     }
     __syncthreads();
-    const int64_t total = (int64_t)B * H * W * 8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int cg = int(i & 7);
-        const int64_t pix = i >> 3;
-        const int x = int(pix % W);
-        const int y = int((pix / W) % H);
-        const int b = int(pix / ((int64_t)W * H));
-        const float* img = spec + (size_t)b * H * W;
+    const int rows = min(kStemRows, H - y0);
+    for (int pix = threadIdx.x >> 2; pix < rows * W; pix += blockDim.x >> 2) {
+        const int ly = pix / W, x = pix - ly * W;
         float tap[9];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int yy = y + dy - 1, xx = x + dx - 1;
-                tap[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[yy * W + xx] : 0.f;
-            }
-        float v[4];
+            for (int dx = 0; dx < 3; ++dx) tap[dy * 3 + dx] = s_in[(ly + dy) * PW + x + dx];
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = cg * 4 + j;
-            float acc = sb[c];
+        for (int j = 0; j < 8; ++j) {
+            float acc = br[j];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc = fmaf(sw[c * 9 + k], tap[k], acc);
-            v[j] = fmaxf(acc, 0.f) * ss[c] + st[c];
+            for (int k = 0; k < 9; ++k) acc = fmaf(wr[j][k], tap[k], acc);
+            v[j] = fmaxf(acc, 0.f) * sr[j] + tr[j];
         }
-        Vec4<T>::store(out + pix * 32 + cg * 4, v);
+        T* o = out + (((size_t)b * H + y0 + ly) * W + x) * 32 + cg * 8;
+        const float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
+        Vec4<T>::store(o, lo);
+        Vec4<T>::store(o + 4, hi);
     }
 }
 
@@ -297,9 +305,9 @@ inline bool ok() { return cudaGetLastError() == cudaSuccess; }
 
 template <class T>
 int launch_stem(const ConvW& c, const float* spec, int B, int H, int W, T* out, cudaStream_t s) {
-    const int64_t total = (int64_t)B * H * W * 8;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-    stem_kernel<T><<<grid, 256, 0, s>>>(spec, B, H, W, c.w32, c.bias, c.scale, c.shift, out);
+    dim3 grid((H + kStemRows - 1) / kStemRows, B);
+    const size_t smem = sizeof(float) * (kStemRows + 2) * (W + 2);
+    stem_kernel<T><<<grid, 256, smem, s>>>(spec, H, W, c.w32, c.bias, c.scale, c.shift, out);
     return ok() ? 1 : -1;
 }
 

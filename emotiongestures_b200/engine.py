@@ -125,7 +125,8 @@ class Engine:
                         "egx_logmel")
         return out
 
-    def generator_forward(self, spec, prior, sampled_emotion=None):
+    def generator_forward(self, spec, prior, sampled_emotion=None, out=None):
+        """`out`: optional preallocated (poses, emo, sem, logits) device tensors (chunked pipelines)."""
         cfg = self.cfg
         if spec.dim() != 3:
             raise RuntimeError("input_spectrum must be (B, n_mels, W)")
@@ -136,10 +137,17 @@ class Engine:
             sampled_emotion = self._f32(sampled_emotion, "sampled_emotion_feature",
                                         (b, cfg.frames, cfg.d_model))
         dev = self.device
-        poses = torch.empty((b, cfg.frames, cfg.pose_dim), dtype=torch.float32, device=dev)
-        emo = torch.empty((b, cfg.frames, cfg.d_model), dtype=torch.float32, device=dev)
-        sem = torch.empty_like(emo)
-        logits = torch.empty((b, 8), dtype=torch.float32, device=dev)
+        if out is not None:
+            poses, emo, sem, logits = out
+            for t, shp in ((poses, (b, cfg.frames, cfg.pose_dim)), (emo, (b, cfg.frames, cfg.d_model)),
+                           (sem, (b, cfg.frames, cfg.d_model)), (logits, (b, 8))):
+                if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                    raise RuntimeError("`out` tensors must be contiguous float32 on the engine device")
+        else:
+            poses = torch.empty((b, cfg.frames, cfg.pose_dim), dtype=torch.float32, device=dev)
+            emo = torch.empty((b, cfg.frames, cfg.d_model), dtype=torch.float32, device=dev)
+            sem = torch.empty_like(emo)
+            logits = torch.empty((b, 8), dtype=torch.float32, device=dev)
         if b == 0:
             return poses, emo, sem, logits
         ws = self.workspace(b)
@@ -150,6 +158,65 @@ class Engine:
                 "egx_generator_forward")
         self._last_b = b
         return poses, emo, sem, logits
+
+    def infer_host(self, audio_h, prior_h, poses_h, chunk: int = 512, mode: int = LOGMEL_LOG_IN,
+                   preemph: bool = True, poses_dev=None):
+        """End-to-end batch from PINNED host buffers: audio_h (B,N), prior_h (B,p,P) -> poses_h (B,F,P).
+
+        The batch is cut into chunks; the host->device copy of chunk i+1, the kernels of chunk i and
+        the device->host copy of chunk i-1 run on three streams, so PCIe time hides behind compute.
+        `poses_dev` (optional, (B,F,P) device tensor) also keeps the poses on the GPU (pose gather).
+        Returns after enqueueing; the caller synchronises (torch.cuda.synchronize / an event).
+        """
+        cfg, dev = self.cfg, self.device
+        b = audio_h.shape[0]
+        if not (audio_h.is_pinned() and prior_h.is_pinned() and poses_h.is_pinned()):
+            raise RuntimeError("infer_host needs pinned host tensors (torch.Tensor.pin_memory())")
+        st = getattr(self, "_pipe", None)
+        if st is None or st["chunk"] < min(chunk, b):
+            c = min(chunk, b)
+            st = self._pipe = {
+                "chunk": c, "h2d": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
+                "audio": [torch.empty((c, audio_h.shape[1]), device=dev) for _ in range(2)],
+                "prior": [torch.empty((c, cfg.prior_frames, cfg.pose_dim), device=dev) for _ in range(2)],
+                "out": [(torch.empty((c, cfg.frames, cfg.pose_dim), device=dev),
+                         torch.empty((c, cfg.frames, cfg.d_model), device=dev),
+                         torch.empty((c, cfg.frames, cfg.d_model), device=dev),
+                         torch.empty((c, 8), device=dev)) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)], "done": [torch.cuda.Event() for _ in range(2)],
+                "in_free": [torch.cuda.Event() for _ in range(2)], "out_free": [torch.cuda.Event() for _ in range(2)],
+            }
+        c = st["chunk"]
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        st["h2d"].wait_event(start)
+        st["d2h"].wait_event(start)
+        for i, lo in enumerate(range(0, b, c)):
+            hi, slot = min(lo + c, b), i & 1
+            n = hi - lo
+            with torch.cuda.stream(st["h2d"]):
+                if i >= 2:
+                    st["h2d"].wait_event(st["in_free"][slot])
+                st["audio"][slot][:n].copy_(audio_h[lo:hi], non_blocking=True)
+                st["prior"][slot][:n].copy_(prior_h[lo:hi], non_blocking=True)
+                st["ready"][slot].record(st["h2d"])
+            main.wait_event(st["ready"][slot])
+            if i >= 2:
+                main.wait_event(st["out_free"][slot])
+            spec = self.logmel(st["audio"][slot][:n], mode, preemph)
+            out = tuple(t[:n] for t in st["out"][slot])
+            self.generator_forward(spec, st["prior"][slot][:n], None, out=out)
+            if poses_dev is not None:
+                poses_dev[lo:hi].copy_(out[0], non_blocking=True)
+            st["in_free"][slot].record(main)
+            st["done"][slot].record(main)
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(st["done"][slot])
+                poses_h[lo:hi].copy_(out[0], non_blocking=True)
+                st["out_free"][slot].record(st["d2h"])
+        main.wait_stream(st["d2h"])
+        return poses_h
 
     # -- parity probes (tests) ----------------------------------------------------
     def tap(self, name: str):
