@@ -31,15 +31,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int kConvThreads = 320;      // producer + MMA + 2 x 4 epilogue warps
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kConvThreads = 384;      // producer + 2 MMA issuers + spare + 2 x 4 epilogue warps
 
 struct ConvTcParams {
     int Ho, Wo;            // output map
     int BW, BH;            // output patch per tile
     int MW;                // row pitch of the M index: BW, or BW + 2 with halo reuse (MW*BH <= 128)
     int tiles_w, tiles_h;
+    int tiles_per_clip;
     int num_tiles;         // B * tiles_h * tiles_w
+    uint32_t magic_tpc, magic_tw;   // ceil(2^40 / d) >> 8 style magics, see fast_div
     int ks, stride, pad;
     int cout;
     int relu_first;
@@ -47,9 +48,13 @@ struct ConvTcParams {
     const float* scale;
     const float* shift;
     __half* out;           // NHWC (B,Ho,Wo,cout) or, if nchw, (B,cout,Ho*Wo)
-    int nchw;
     float* se_part;        // [B][tiles_h*tiles_w][cout] partial channel sums, or null
+    int debug;             // EGX_CONV_DEBUG (attribution experiments only): 1 = no epilogue work, 2 = no TMA loads
 };
+
+// n / d for n*d < 2^32 with magic = ceil(2^32 / d) (d >= 2), exact by the usual round-up argument
+__host__ __device__ __forceinline__ uint32_t make_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 
 // HALO (stride-1 3x3 with resident weights): instead of nine shifted boxes per tile, ONE box per 64-channel
 // chunk brings the (BH+2) x (BW+2) input patch; the M index runs over BH x (BW+2) positions (two junk
@@ -58,7 +63,12 @@ struct ConvTcParams {
 // bits, so a row-shifted descriptor still sees the pattern TMA wrote.  L2->SM traffic per tile drops ~7x.
 constexpr int kPatchRows = 176;          // >= 128 + 2*(BW+2) + 2 with BW + 2 <= 20
 
-template <int CIN, int NPAD, int TAPS, bool HALO = false>
+// Output path of the epilogue
+enum { OUT_TMA = 0,      // NHWC fp16 through a swizzled shared-memory staging tile and one TMA box store per tile
+       OUT_DIRECT = 1,   // NHWC fp16, each thread stores its pixel's channels (>= 128 contiguous bytes)
+       OUT_NCHW = 2 };   // (B,cout,Ho*Wo) fp16 (final conv: the A operand of fc1), bias supported
+
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
 struct ConvCfg {
     static constexpr int CK = CIN < 64 ? CIN : 64;           // channels per K block
     static constexpr int kSwz = CK * 2;                      // 64 or 128 byte rows
@@ -73,52 +83,89 @@ struct ConvCfg {
     static constexpr int kStageBytes = HALO ? kChunks * kPatchBytes
                                             : kKbPerStage * (kABytes + (kResidentB ? 0 : kBBytes));
     static constexpr int kResBytes = kResidentB ? kNumKb * kBBytes : 0;
-    static constexpr int kStagesRaw = (kSmemBudget - kResBytes) / kStageBytes;
+    // output staging: [group][buffer] tiles of 128 rows x NPAD fp16 (rows of 64 / 128 bytes, TMA-store swizzle)
+    static constexpr int kOutRowBytes = NPAD * 2;
+    static constexpr int kOutTileBytes = 128 * kOutRowBytes;
+    static constexpr int kOutBytes = OUT == OUT_TMA ? 4 * kOutTileBytes : 0;
+    static constexpr int kTailBytes = 256 + 3 * 128 * 4 + 2 * 2 * 4 * 128 * 4 + 1024;   // barriers, params, SE sums, align
+    static constexpr int kSmemBudget = 227 * 1024 - 512;
+    static constexpr int kStagesRaw = (kSmemBudget - kResBytes - kOutBytes - kTailBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kStagesPerTile = kNumKb / kKbPerStage;
-    static constexpr int kBarOffset = kResBytes + kStages * kStageBytes;
+    static constexpr int kOutOffset = kResBytes + kStages * kStageBytes;
+    static constexpr int kBarOffset = kOutOffset + kOutBytes;
     static constexpr int kParOffset = kBarOffset + 256;      // bias | scale | shift, 128 floats each
-    static constexpr int kRedOffset = kParOffset + 3 * 128 * 4;   // 2 groups x 4 warps x 128 floats (SE sums)
-    static constexpr int kTotal = kRedOffset + 2 * 4 * 128 * 4 + 1024;
+    static constexpr int kRedOffset = kParOffset + 3 * 128 * 4;   // [group][parity][4 warps][128] floats (SE sums)
+    static constexpr int kTotal = kRedOffset + 2 * 2 * 4 * 128 * 4 + 1024;
     static constexpr int kAccStride = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128);
-    static constexpr uint32_t kTmemCols = 2 * kAccStride;
+    static constexpr uint32_t kTmemCols = 4 * kAccStride;    // four accumulator buffers
+    static constexpr bool kTwoIssuers = HALO;                // see the MMA section
     static_assert(kNumKb % kKbPerStage == 0, "stage must divide the K loop");
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
     static_assert(!HALO || (TAPS == 9 && kResidentB), "halo reuse needs a 3x3 conv with resident weights");
+    static_assert(OUT != OUT_TMA || NPAD == 32 || NPAD == 64, "TMA-store staging rows are one swizzle span");
+    static_assert((kStageBytes % 1024) == 0 && (kResBytes % 1024) == 0, "swizzle atoms need 1024-byte alignment");
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n)); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int CIN, int NPAD, int TAPS, bool HALO>
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
-    using S = ConvCfg<CIN, NPAD, TAPS, HALO>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, ConvTcParams p) {
+    using S = ConvCfg<CIN, NPAD, TAPS, HALO, OUT>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // keep everything an offset from the __shared__ array so that loads/stores stay in the shared window
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
     unsigned char* ring = smem + S::kResBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
     uint64_t* empty = full + S::kStages;
-    uint64_t* tmem_full = empty + S::kStages;      // [2]
-    uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint64_t* b_full = tmem_empty + 2;
+    uint64_t* tmem_full = empty + S::kStages;      // [4]
+    uint64_t* tmem_empty = tmem_full + 4;          // [4]
+    uint64_t* b_full = tmem_empty + 4;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
     float* par = reinterpret_cast<float*>(smem + S::kParOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_clip = p.tiles_w * p.tiles_h;
+    const int tiles_per_clip = p.tiles_per_clip;
     constexpr int KS = TAPS == 9 ? 3 : 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (OUT == OUT_TMA) prefetch_tmap(&tmO);
         for (int i = 0; i < S::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_ptr);
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
-        const int n = threadIdx.x - 64;
+    if (warp == 3) tmem_alloc<S::kTmemCols>(tmem_ptr);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + 128) {
+        const int n = threadIdx.x - 128;
         par[n] = (p.bias && n < p.cout) ? p.bias[n] : 0.f;
         par[128 + n] = n < p.cout ? p.scale[n] : 0.f;
         par[256 + n] = n < p.cout ? p.shift[n] : 0.f;
@@ -148,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int st = it % S::kStages;
                     mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
                     unsigned char* dst = ring + st * S::kStageBytes;
+                    if (p.debug & 2) { mbar_arrive(&full[st]); ++it; continue; }
                     mbar_expect_tx(&full[st], (uint32_t)S::kChunks * p.MW * (p.BH + 2) * S::kSwz);
 #pragma unroll
                     for (int ch = 0; ch < S::kChunks; ++ch)
@@ -159,6 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int st = it % S::kStages;
                     mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
                     unsigned char* dst = ring + st * S::kStageBytes;
+                    if (p.debug & 2) { mbar_arrive(&full[st]); continue; }
                     mbar_expect_tx(&full[st], stage_tx);
 #pragma unroll
                     for (int j = 0; j < S::kKbPerStage; ++j) {
@@ -173,113 +222,184 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (elect_one()) {
+    } else if (warp == 1 || warp == 2) {
+        // ================= MMA issuers =================
+        // Four TMEM accumulator buffers (tile n of this CTA -> buffer n & 3), so a tile's MMAs never wait for the
+        // epilogue of the tile two before it.  A 128xNx16 MMA with N <= 64 drains in 40-48 cycles (shared-memory
+        // operand reads: (128 + N) rows x 32 B at 128 B/clk) but costs its issuing thread ~45 cycles, and every
+        // mbarrier wait ~180 cycles even when the phase is already complete, so a single issuer can never build
+        // up a queue and each wait is a bubble in the tensor pipe.  Where one tile is one ring stage (HALO) two
+        // warps issue: warp 1 the CTA's even tiles, warp 2 the odd ones; their waits overlap the other's MMAs.
+        // (Multi-stage tiles keep one issuer: parity waits on a ring stage may not run several phases ahead.)
+        const uint32_t issuer = warp - 1;
+        if ((S::kTwoIssuers || issuer == 0) && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, NPAD);
+            constexpr uint32_t kDescHi = smem_desc_hi<S::kSwz>();
+            const uint32_t b_lo = smem_desc_lo(smem_u32(smem));                 // resident weights start at smem + 0
+            const uint32_t row_off[3] = {0u, (uint32_t)(p.MW * S::kSwz) >> 4, (uint32_t)(2 * p.MW * S::kSwz) >> 4};
             if (S::kResidentB) { mbar_wait(b_full, 0); tc_fence_after(); }
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1;
-                mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            constexpr uint32_t kStep = S::kTwoIssuers ? 2 : 1;
+            uint32_t tcount = S::kTwoIssuers ? issuer : 0;
+            for (int tile = blockIdx.x + tcount * gridDim.x; tile < p.num_tiles; tile += kStep * gridDim.x, tcount += kStep) {
+                uint32_t it = tcount * (HALO ? 1 : S::kStagesPerTile);
+                const uint32_t acc = tcount & 3;
+                mbar_wait(&tmem_empty[acc], ((tcount >> 2) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * S::kAccStride;
                 if (HALO) {
                     const int st = it % S::kStages;
                     mbar_wait(&full[st], (it / S::kStages) & 1);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(ring + st * S::kStageBytes);
+                    const uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * S::kStageBytes));
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t shift = (uint32_t)((tap / 3) * p.MW + (tap % 3)) * S::kSwz;
+                        const uint32_t a_tap = a_lo + row_off[tap / 3] + (tap % 3) * (S::kSwz >> 4);
 #pragma unroll
                         for (int ch = 0; ch < S::kChunks; ++ch) {
-                            const uint32_t a = a0 + ch * S::kPatchBytes + shift;
-                            const uint32_t bb = smem_u32(smem + (tap * S::kChunks + ch) * S::kBBytes);
 #pragma unroll
                             for (int k = 0; k < S::CK / 16; ++k)
-                                umma_f16(d, make_smem_desc<S::kSwz>(a + k * 32), make_smem_desc<S::kSwz>(bb + k * 32),
-                                         idesc, (tap | ch | k) != 0);
+                                umma_f16_lo<kDescHi>(d, a_tap + ((ch * S::kPatchBytes + k * 32) >> 4),
+                                                     b_lo + (((tap * S::kChunks + ch) * S::kBBytes + k * 32) >> 4), idesc,
+                                                     (tap | ch | k) != 0);
                         }
                     }
                     umma_commit(&empty[st]);
                     umma_commit(&tmem_full[acc]);
-                    ++it;
                     continue;
                 }
                 for (int sg = 0; sg < S::kStagesPerTile; ++sg, ++it) {
                     const int st = it % S::kStages;
                     mbar_wait(&full[st], (it / S::kStages) & 1);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(ring + st * S::kStageBytes);
+                    const uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * S::kStageBytes));
 #pragma unroll
                     for (int j = 0; j < S::kKbPerStage; ++j) {
                         const int kb = sg * S::kKbPerStage + j;
-                        const uint32_t a = a0 + j * S::kABytes;
-                        const uint32_t bb = S::kResidentB ? smem_u32(smem + kb * S::kBBytes)
-                                                          : a0 + S::kKbPerStage * S::kABytes + j * S::kBBytes;
+                        const uint32_t bb = S::kResidentB ? b_lo + ((kb * S::kBBytes) >> 4)
+                                                          : a_lo + ((S::kKbPerStage * S::kABytes + j * S::kBBytes) >> 4);
 #pragma unroll
                         for (int k = 0; k < S::CK / 16; ++k)
-                            umma_f16(d, make_smem_desc<S::kSwz>(a + k * 32), make_smem_desc<S::kSwz>(bb + k * 32),
-                                     idesc, (kb | k) != 0);
+                            umma_f16_lo<kDescHi>(d, a_lo + ((j * S::kABytes + k * 32) >> 4), bb + ((k * 32) >> 4), idesc,
+                                                 (kb | k) != 0);
                     }
                     umma_commit(&empty[st]);
                 }
                 umma_commit(&tmem_full[acc]);
             }
         }
-    } else {
+    } else if (warp >= 4) {
         // ================= epilogue =================
-        const int grp = (warp - 2) >> 2;          // accumulator buffer / tile parity this group drains
+        const int grp = (warp - 4) >> 2;          // accumulator buffer / tile parity this group drains
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;
+        const int r = q * 32 + lane;              // accumulator row = M index of this thread's pixel
         const int ph_ = r / p.MW, pw_ = r % p.MW;
-        float* red = reinterpret_cast<float*>(smem + S::kRedOffset) + grp * 512;
+        const bool in_patch = ph_ < p.BH && pw_ < p.BW;
+        const int orow = ph_ * p.BW + pw_;        // row of the dense BH x BW output box
         const bool relu_first = p.relu_first != 0;
-        uint32_t tcount = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, tcount += 2) {
-            const int b = tile / tiles_per_clip;
-            const int t = tile - b * tiles_per_clip;
-            const int ho = (t / p.tiles_w) * p.BH + ph_, wo = (t % p.tiles_w) * p.BW + pw_;
-            const bool valid = ph_ < p.BH && pw_ < p.BW && ho < p.Ho && wo < p.Wo;
-            mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
+        const bool has_bias = p.bias != nullptr;
+        const bool se = p.se_part != nullptr;
+        const uint32_t par_u32 = smem_u32(par);
+        const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
+        // staging row of this thread with the TMA-store swizzle (16-byte chunk index XOR row bits)
+        const uint32_t stage_u32 = smem_u32(smem + S::kOutOffset) + grp * 2 * S::kOutTileBytes + orow * S::kOutRowBytes;
+        const uint32_t swz_x = S::kOutRowBytes == 64 ? ((orow >> 1) & 3) : (orow & 7);
+        // copy-out assignment of this thread (tile-invariant): chunk id = i * 128 + r -> (row, 16-byte chunk)
+        constexpr int kChunksPerRow = S::kOutRowBytes / 16;
+        constexpr int kCopyIters = OUT == OUT_TMA ? kChunksPerRow : 1;
+        int cp_ph[kCopyIters], cp_pw[kCopyIters];
+        uint32_t cp_src[kCopyIters], cp_dst[kCopyIters];
+#pragma unroll
+        for (int i = 0; i < kCopyIters; ++i) {
+            const int id = i * 128 + r, row = id / kChunksPerRow, ck = id % kChunksPerRow;
+            cp_ph[i] = row < p.BH * p.BW ? row / p.BW : -1;
+            cp_pw[i] = row % p.BW;
+            cp_src[i] = row * S::kOutRowBytes + ((ck ^ (S::kOutRowBytes == 64 ? ((row >> 1) & 3) : (row & 7))) << 4);
+            cp_dst[i] = (uint32_t)((cp_ph[i] * p.Wo + cp_pw[i]) * S::kOutRowBytes + ck * 16);
+        }
+        // NPAD == 32: the folded BatchNorm parameters of all channels live in registers
+        float sc_r[NPAD == 32 ? 32 : 1], sh_r[NPAD == 32 ? 32 : 1];
+        if (NPAD == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { sc_r[j] = par[128 + j]; sh_r[j] = par[256 + j]; }
+        }
+        uint32_t tcount = grp, n_local = 0;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, tcount += 2, ++n_local) {
+            const uint32_t b = fast_div((uint32_t)tile, p.magic_tpc);
+            const uint32_t t = (uint32_t)tile - b * tiles_per_clip;
+            const uint32_t th = fast_div(t, p.magic_tw);
+            const uint32_t tw = t - th * p.tiles_w;
+            const int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
+            const bool valid = in_patch && ho < p.Ho && wo < p.Wo;
+            const uint32_t par_buf = n_local & 1;
+            const uint32_t acc = tcount & 3;
+            mbar_wait(&tmem_full[acc], (tcount >> 2) & 1);
             tc_fence_after();
-            const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
-            const uint32_t taddr = tmem_base + grp * S::kAccStride + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * S::kAccStride + ((uint32_t)(q * 32) << 16);
+            if (p.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < (NPAD + 31) / 32; ++c) {
                 float v[32];
                 __syncwarp();
                 tmem_ld32(taddr + c * 32, v);
                 const int nb = c * 32;
+                if (has_bias) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 bi = *reinterpret_cast<const float4*>(par + nb + 4 * j4);
-                    const float4 sc = *reinterpret_cast<const float4*>(par + 128 + nb + 4 * j4);
-                    const float4 sh = *reinterpret_cast<const float4*>(par + 256 + nb + 4 * j4);
-                    const float bv[4] = {bi.x, bi.y, bi.z, bi.w}, sv[4] = {sc.x, sc.y, sc.z, sc.w},
-                                hv[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float tv = v[4 * j4 + e] + bv[e];
-                        if (relu_first) tv = fmaxf(tv, 0.f);
-                        tv = fmaf(tv, sv[e], hv[e]);
-                        v[4 * j4 + e] = valid ? tv : 0.f;
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bi = lds128(par_u32 + (nb + 4 * j4) * 4);
+                        v[4 * j4] += bi.x; v[4 * j4 + 1] += bi.y; v[4 * j4 + 2] += bi.z; v[4 * j4 + 3] += bi.w;
                     }
                 }
-                if (valid) {
-                    if (!p.nchw) {
-                        __half* o = p.out + pix * p.cout + nb;     // cout is a multiple of 32 on this path
+                if (NPAD == 32) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-                            *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                            *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                            *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                            reinterpret_cast<uint4*>(o)[j] = u;
+                    for (int j = 0; j < 32; ++j) {
+                        float tv = v[j];
+                        if (relu_first) tv = fmaxf(tv, 0.f);
+                        v[j] = fmaf(tv, sc_r[j], sh_r[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 sc = lds128(par_u32 + (128 + nb + 4 * j4) * 4);
+                        const float4 sh = lds128(par_u32 + (256 + nb + 4 * j4) * 4);
+                        const float sv[4] = {sc.x, sc.y, sc.z, sc.w}, hv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float tv = v[4 * j4 + e];
+                            if (relu_first) tv = fmaxf(tv, 0.f);
+                            v[4 * j4 + e] = fmaf(tv, sv[e], hv[e]);
                         }
-                    } else {
+                    }
+                }
+                if (OUT == OUT_TMA) {
+                    if (in_patch) {
+                        const uint32_t row = stage_u32 + par_buf * S::kOutTileBytes;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            sts128(row + (((uint32_t)(c * 4 + j) ^ swz_x) << 4), pack_h2(v[8 * j], v[8 * j + 1]),
+                                   pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+                                   pack_h2(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                } else if (OUT == OUT_DIRECT) {
+                    if (valid) {
+                        const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
+                        __half* o = p.out + pix * p.cout + nb;     // cout is a multiple of 32 on this path
+                        // 256-bit stores: every thread writes whole 32-byte sectors
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 16 * j),
+                                         "r"(pack_h2(v[16 * j], v[16 * j + 1])), "r"(pack_h2(v[16 * j + 2], v[16 * j + 3])),
+                                         "r"(pack_h2(v[16 * j + 4], v[16 * j + 5])), "r"(pack_h2(v[16 * j + 6], v[16 * j + 7])),
+                                         "r"(pack_h2(v[16 * j + 8], v[16 * j + 9])), "r"(pack_h2(v[16 * j + 10], v[16 * j + 11])),
+                                         "r"(pack_h2(v[16 * j + 12], v[16 * j + 13])), "r"(pack_h2(v[16 * j + 14], v[16 * j + 15]))
+                                         : "memory");
+                    }
+                } else {
+                    if (valid) {
                         const size_t hw = (size_t)p.Ho * p.Wo;
                         __half* o = p.out + (size_t)b * p.cout * hw + (size_t)ho * p.Wo + wo;
 #pragma unroll
@@ -287,9 +407,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (nb + j < p.cout) o[(size_t)(nb + j) * hw] = __float2half_rn(v[j]);
                     }
                 }
-                if (p.se_part) {
+                if (se) {
                     // column sums over the warp's 32 rows: butterfly "transpose-reduce", 31 shuffles for 32 columns;
                     // lane l ends up holding the sum of column nb + l
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
 #pragma unroll
                     for (int step = 16; step >= 1; step >>= 1) {
                         const bool upper = (lane & step) != 0;
@@ -300,25 +424,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
                         }
                     }
-                    red[q * 128 + nb + lane] = v[0];
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red_u32 + (par_buf * 512 + q * 128 + nb + lane) * 4), "f"(v[0]) : "memory");
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[grp]);
-            if (p.se_part) {
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (OUT == OUT_TMA || se) {
                 named_bar_sync(1 + grp, 128);
-                const int n = q * 32 + lane;
-                if (n < p.cout)
-                    p.se_part[((size_t)b * tiles_per_clip + t) * p.cout + n] =
-                        (red[n] + red[128 + n]) + (red[256 + n] + red[384 + n]);
-                named_bar_sync(1 + grp, 128);
+                if (OUT == OUT_TMA && !(p.debug & 16)) {
+                    // copy-out: consecutive threads move consecutive 16-byte chunks of the staged tile, so a warp
+                    // writes 512 contiguous bytes of an image row (full sectors, no TMA descriptor work)
+                    const uint32_t src0 = smem_u32(smem + S::kOutOffset) + (grp * 2 + par_buf) * S::kOutTileBytes;
+                    const int h0 = (int)th * p.BH, w0 = (int)tw * p.BW;
+                    __half* tile_out = p.out + (((size_t)b * p.Ho + h0) * p.Wo + w0) * NPAD;
+#pragma unroll
+                    for (int i = 0; i < kCopyIters; ++i) {
+                        if (cp_ph[i] >= 0 && h0 + cp_ph[i] < p.Ho && w0 + cp_pw[i] < p.Wo) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(src0 + cp_src[i]));
+                            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(tile_out) + cp_dst[i]) = u;
+                        }
+                    }
+                }
+                if (se) {
+                    const int n = q * 32 + lane;
+                    if (n < p.cout) {
+                        const float* red = reinterpret_cast<const float*>(smem + S::kRedOffset) + grp * 1024 + par_buf * 512;
+                        p.se_part[(size_t)tile * p.cout + n] = (red[n] + red[128 + n]) + (red[256 + n] + red[384 + n]);
+                    }
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<S::kTmemCols>(tmem_base);
+    if (warp == 3) tmem_dealloc<S::kTmemCols>(tmem_base);
 }
 
 // (BW, BH) with BW*BH <= 128 that wastes the fewest MMA rows on an Ho x Wo map
@@ -346,12 +488,13 @@ void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
 }
 
 int g_num_sms = 0;
-int g_halo = 1;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
+int g_debug = 0;
+int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too
+int g_halo = 3;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
 
-template <int CIN, int NPAD, int TAPS, bool HALO>
-int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw, float* se_part,
-               cudaStream_t s) {
-    using S = ConvCfg<CIN, NPAD, TAPS, HALO>;
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
+int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, cudaStream_t s) {
+    using S = ConvCfg<CIN, NPAD, TAPS, HALO, OUT>;
     ConvTcParams p;
     p.ks = c.ks; p.stride = c.stride; p.pad = c.ks / 2;
     p.Ho = (Hin + 2 * p.pad - c.ks) / c.stride + 1;
@@ -361,12 +504,16 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     p.MW = HALO ? p.BW + 2 : p.BW;
     p.tiles_w = (p.Wo + p.BW - 1) / p.BW;
     p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
-    p.num_tiles = B * p.tiles_w * p.tiles_h;
+    p.tiles_per_clip = p.tiles_w * p.tiles_h;
+    p.num_tiles = B * p.tiles_per_clip;
+    if ((uint64_t)p.num_tiles * (uint64_t)p.tiles_per_clip >= (1ull << 32)) return -1;   // fast_div exactness
+    p.magic_tpc = make_magic((uint32_t)p.tiles_per_clip);
+    p.magic_tw = make_magic((uint32_t)p.tiles_w);
     p.cout = c.cout; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
-    p.out = out; p.nchw = nchw; p.se_part = se_part;
+    p.out = out; p.se_part = se_part; p.debug = g_debug;
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to;
     const uint64_t dA[4] = {(uint64_t)CIN, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     const uint64_t sA[3] = {(uint64_t)CIN * 2, (uint64_t)Win * CIN * 2, (uint64_t)Hin * Win * CIN * 2};
     // with an element (traversal) stride e the box spans boxDim positions and keeps ceil(boxDim / e) of them
@@ -380,33 +527,61 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     const uint64_t sB[1] = {(uint64_t)K * 2};
     const uint32_t bB[2] = {(uint32_t)S::CK, (uint32_t)NPAD};
     if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, swz)) return -1;
+    if (OUT == OUT_TMA) {
+        if (c.cout != NPAD) return -1;
+        const uint64_t dO[4] = {(uint64_t)NPAD, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)B};
+        const uint64_t sO[3] = {(uint64_t)NPAD * 2, (uint64_t)p.Wo * NPAD * 2, (uint64_t)p.Ho * p.Wo * NPAD * 2};
+        const uint32_t bO[4] = {(uint32_t)NPAD, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        if (!make_tmap_f16(&to, out, 4, dO, sO, bO, nullptr,
+                           NPAD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+            return -1;
+    } else {
+        to = ta;
+    }
     const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-    conv_tc_kernel<CIN, NPAD, TAPS, HALO><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, p);
+    conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, to, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-template <int CIN, int NPAD, int TAPS, bool HALO = false>
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
 int set_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<CIN, NPAD, TAPS, HALO>::kTotal) == cudaSuccess ? 0 : -1;
+    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<CIN, NPAD, TAPS, HALO, OUT>::kTotal) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
+
+// every instantiation: (cin, npad, taps, halo, out)
+#define EGX_CONV_INSTANCES(X)                                                                         \
+    X(32, 32, 9, true, OUT_TMA) X(32, 32, 9, false, OUT_TMA) X(64, 64, 9, true, OUT_TMA)              \
+    X(64, 64, 9, false, OUT_TMA) X(32, 64, 9, false, OUT_TMA) X(32, 64, 1, false, OUT_TMA)            \
+    X(64, 128, 9, false, OUT_DIRECT) X(64, 128, 1, false, OUT_DIRECT) X(128, 128, 9, false, OUT_DIRECT) \
+    X(32, 32, 9, true, OUT_DIRECT) X(64, 64, 9, true, OUT_DIRECT)                                     \
+    X(128, 48, 9, false, OUT_NCHW) X(128, 64, 9, false, OUT_NCHW)
 
 int conv_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     if (const char* e = getenv("EGX_CONV_HALO")) g_halo = atoi(e);
-    return set_attr<32, 32, 9>() | set_attr<32, 64, 9>() | set_attr<64, 64, 9>() | set_attr<64, 128, 9>() |
-           set_attr<128, 128, 9>() | set_attr<128, 48, 9>() | set_attr<128, 64, 9>() | set_attr<32, 64, 1>() |
-           set_attr<64, 128, 1>() | set_attr<32, 32, 9, true>() | set_attr<64, 64, 9, true>();
+    if (const char* e = getenv("EGX_CONV_DEBUG")) g_debug = atoi(e);
+    if (const char* e = getenv("EGX_CONV_OUT")) g_out_direct = atoi(e);
+    int rc = 0;
+#define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU>();
+    EGX_CONV_INSTANCES(X)
+#undef X
+    return rc;
+}
+
+static bool use_halo(int cin, int cout, int ks, int stride, int nchw) {
+    if (ks != 3 || stride != 1 || nchw || cin != cout) return false;
+    return (cin == 64 && g_halo >= 1) || (cin == 32 && (g_halo & 2));
 }
 
 // SE partial-sum slots a conv writes per clip (tiles per clip) for an Ho x Wo output map
 int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo) {
     int bw, bh;
-    if (g_halo && cin == cout && (cin == 64 || (cin == 32 && g_halo > 1))) pick_halo_patch(Ho, Wo, &bw, &bh);
+    if (use_halo(cin, cout, 3, 1, 0)) pick_halo_patch(Ho, Wo, &bw, &bh);
     else pick_patch(Ho, Wo, &bw, &bh);
     return ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
 }
@@ -417,24 +592,13 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
                    cudaStream_t s) {
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
     if (c.cout > 128 || (!nchw && c.cout % 32)) return -1;
-    if (g_halo && c.ks == 3 && c.stride == 1 && !nchw) {
-        // cin = 32 is bound by the MMA's shared-memory operand reads (N = 32), where the halo variant's extra
-        // junk columns cost more than the L2 traffic it saves: measured 546 vs 513 us/launch; EGX_CONV_HALO=2 forces it
-        if (c.cin == 32 && c.cout == 32 && g_halo > 1) return launch_one<32, 32, 9, true>(c, in, B, Hin, Win, out, nchw, se_part, s);
-        if (c.cin == 64 && c.cout == 64) return launch_one<64, 64, 9, true>(c, in, B, Hin, Win, out, nchw, se_part, s);
-    }
-#define EGX_CONV_CASE(CI, NP, TP) \
-    if (c.cin == CI && npad == NP && c.ks * c.ks == TP) return launch_one<CI, NP, TP, false>(c, in, B, Hin, Win, out, nchw, se_part, s);
-    EGX_CONV_CASE(32, 32, 9)
-    EGX_CONV_CASE(32, 64, 9)
-    EGX_CONV_CASE(64, 64, 9)
-    EGX_CONV_CASE(64, 128, 9)
-    EGX_CONV_CASE(128, 128, 9)
-    EGX_CONV_CASE(128, 48, 9)
-    EGX_CONV_CASE(128, 64, 9)
-    EGX_CONV_CASE(32, 64, 1)
-    EGX_CONV_CASE(64, 128, 1)
-#undef EGX_CONV_CASE
+    const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
+    const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & 2))))) ? OUT_TMA : OUT_DIRECT);
+#define X(CI, NP, TP, HL, OU)                                                                   \
+    if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU)         \
+        return launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, s);
+    EGX_CONV_INSTANCES(X)
+#undef X
     return -1;
 }
 

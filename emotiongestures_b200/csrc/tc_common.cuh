@@ -88,6 +88,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Pure polling variant (mbarrier.test_wait never suspends the thread): lowest wake-up latency, for the single
+// producer / MMA-issuer threads whose hand-offs sit on the critical path.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spins > (1u << 28)) __trap();
+    }
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -149,6 +166,34 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// Issue-cost matters: ONE thread feeds the tensor pipe, and a 128xNx16 MMA with N <= 64 retires every ~45 cycles,
+// so the descriptor arithmetic around each MMA has to stay at two or three (uniform-datapath) instructions.
+// The descriptor's high word is a constant; the low word is (addr >> 4) | (1 << 16), and moving the start
+// address by `bytes` is `lo + (bytes >> 4)` (the 14-bit address field cannot overflow below 256 KB).
+template <int kSwizzleBytes>
+__host__ __device__ constexpr uint32_t smem_desc_hi() {
+    return (uint32_t)((8 * kSwizzleBytes) >> 4) | (1u << 14) | ((kSwizzleBytes == 128 ? 2u : (kSwizzleBytes == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+
+template <uint32_t kDescHi>
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+    if (accumulate)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc)
+            : "memory");
 }
 
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
