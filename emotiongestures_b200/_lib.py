@@ -46,6 +46,16 @@ PROTOTYPES = {
                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "egx_debug_attention_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "egx_cvae_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "egx_cvae_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "egx_cvae3_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "egx_pose_features": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
+    "egx_pose_feature_dim": (C.c_int, [C.c_void_p, C.c_int]),
+    "egx_row_features_workspace": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "egx_row_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
     "egx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "egx_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "egx_launch_count": (C.c_int64, [C.c_void_p]),

@@ -22,7 +22,7 @@ T* upload(egx_handle* h, const std::vector<T>& v) {
     if (cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)) != cudaSuccess) return nullptr;
     if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
         return nullptr;
-    h->owned.push_back(p);
+    (h->cur_bucket ? *h->cur_bucket : h->owned).push_back(p);
     return static_cast<T*>(p);
 }
 
@@ -692,6 +692,244 @@ int debug_trunk_tc(egx_handle* h, const float* spec, int B, int stage, float* ou
 
 }  // namespace
 
+
+// ---------------------------------------------------------------------------------------------
+// small networks: eval-mode algebra folded in float64 on the host
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Affine {
+    int in = 0, out = 0;
+    std::vector<double> W, b;     // W[out][in]
+};
+
+bool get_affine(egx_handle* h, const std::string& pre, int in, int out, Affine* a) {
+    const HostTensor *w, *b;
+    if (!need(h, pre + ".weight", {out, in}, &w) || !need(h, pre + ".bias", {out}, &b)) return false;
+    a->in = in; a->out = out;
+    a->W.assign(w->v.begin(), w->v.end());
+    a->b.assign(b->v.begin(), b->v.end());
+    return true;
+}
+
+// second(first(x))
+Affine compose(const Affine& first, const Affine& second) {
+    Affine r;
+    r.in = first.in; r.out = second.out;
+    r.W.assign((size_t)r.out * r.in, 0.0);
+    r.b = second.b;
+    for (int o = 0; o < second.out; ++o)
+        for (int m = 0; m < second.in; ++m) {
+            const double s = second.W[(size_t)o * second.in + m];
+            r.b[o] += s * first.b[m];
+            for (int i = 0; i < first.in; ++i) r.W[(size_t)o * r.in + i] += s * first.W[(size_t)m * first.in + i];
+        }
+    return r;
+}
+
+// y = x * s + t for an eval-mode BatchNorm1d under `pre`
+bool bn_scale_shift(egx_handle* h, const std::string& pre, int c, std::vector<double>& s, std::vector<double>& t) {
+    const HostTensor *g, *b, *m, *v;
+    if (!need(h, pre + ".weight", {c}, &g) || !need(h, pre + ".bias", {c}, &b) ||
+        !need(h, pre + ".running_mean", {c}, &m) || !need(h, pre + ".running_var", {c}, &v))
+        return false;
+    s.resize(c); t.resize(c);
+    for (int i = 0; i < c; ++i) {
+        s[i] = (double)g->v[i] / std::sqrt((double)v->v[i] + (double)kBnEps);
+        t[i] = (double)b->v[i] - (double)m->v[i] * s[i];
+    }
+    return true;
+}
+
+void scale_rows(Affine& a, const std::vector<double>& s, const std::vector<double>& t) {   // BN after a Linear
+    for (int o = 0; o < a.out; ++o) {
+        for (int i = 0; i < a.in; ++i) a.W[(size_t)o * a.in + i] *= s[o];
+        a.b[o] = a.b[o] * s[o] + t[o];
+    }
+}
+
+std::vector<float> to_f32(const std::vector<double>& v) { return std::vector<float>(v.begin(), v.end()); }
+
+// chain of Linears at Sequential indices idx[] under `pre` (the Dropouts between them are identities in eval)
+bool linear_chain(egx_handle* h, const std::string& pre, std::initializer_list<int> idx, std::initializer_list<int> dims, Affine* out) {
+    auto d = dims.begin();
+    bool first = true;
+    for (int i : idx) {
+        Affine a;
+        if (!get_affine(h, pre + "." + std::to_string(i), d[0], d[1], &a)) return false;
+        *out = first ? a : compose(*out, a);
+        first = false;
+        ++d;
+    }
+    return true;
+}
+
+struct BucketScope {
+    egx_handle* h;
+    BucketScope(egx_handle* hh, const std::string& family) : h(hh) {
+        auto& b = h->aux_owned[family];
+        for (void* p : b) cudaFree(p);
+        b.clear();
+        h->cur_bucket = &b;
+    }
+    ~BucketScope() { h->cur_bucket = nullptr; }
+    bool ok() const {
+        for (void* p : *h->cur_bucket) if (!p) return false;
+        return true;
+    }
+};
+
+// C4: Full_model/BEAT_CVAE.py:32-83 (layers), :98-136 (forward / sample)
+int pack_cvae(egx_handle* h) {
+    BucketScope scope(h, "cvae");
+    h->cvae = CvaeW();
+    Affine enc, mu, lv, py, fus, dec;
+    if (!linear_chain(h, "cvae.Encoder", {0, 2, 4, 6, 8}, {90, 128, 128, 256, 256, 512}, &enc)) return 1;
+    if (!get_affine(h, "cvae.fc_mu", 512, 32, &mu) || !get_affine(h, "cvae.fc_var", 512, 32, &lv)) return 1;
+    if (!linear_chain(h, "cvae.Posterior_Y_embedding", {0, 2}, {90, 64, 32}, &py)) return 1;
+    if (!linear_chain(h, "cvae.fusion_z_posterior", {0, 2}, {64, 256, 512}, &fus)) return 1;
+    if (!linear_chain(h, "cvae.Decoder", {0, 2, 4, 6, 8}, {512, 256, 256, 128, 128, 90}, &dec)) return 1;
+    const Affine xmu = compose(enc, mu), xlv = compose(enc, lv), zd = compose(fus, dec);
+    std::vector<float> w_x(90 * 64), b_x(64), w_y(90 * 32), b_y(32), w_d(64 * 92, 0.f), b_d(92, 0.f);
+    for (int k = 0; k < 90; ++k)
+        for (int o = 0; o < 32; ++o) {
+            w_x[k * 64 + o] = (float)xmu.W[(size_t)o * 90 + k];
+            w_x[k * 64 + 32 + o] = (float)xlv.W[(size_t)o * 90 + k];
+            w_y[k * 32 + o] = (float)py.W[(size_t)o * 90 + k];
+        }
+    for (int o = 0; o < 32; ++o) { b_x[o] = (float)xmu.b[o]; b_x[32 + o] = (float)xlv.b[o]; b_y[o] = (float)py.b[o]; }
+    for (int k = 0; k < 64; ++k)
+        for (int o = 0; o < 90; ++o) w_d[k * 92 + o] = (float)zd.W[(size_t)o * 64 + k];
+    for (int o = 0; o < 90; ++o) b_d[o] = (float)zd.b[o];
+    CvaeW& c = h->cvae;
+    c.w_x = upload(h, w_x); c.b_x = upload(h, b_x); c.w_y = upload(h, w_y); c.b_y = upload(h, b_y);
+    c.w_d = upload(h, w_d); c.b_d = upload(h, b_d);
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing cvae weights");
+    c.ready = true;
+    return 0;
+}
+
+bool upload_tensor(egx_handle* h, const std::string& key, std::initializer_list<int64_t> shape, float** out) {
+    const HostTensor* t;
+    if (!need(h, key, shape, &t)) return false;
+    *out = upload(h, t->v);
+    return true;
+}
+
+bool upload_bn(egx_handle* h, const std::string& pre, int c, float** s_out, float** t_out) {
+    std::vector<double> s, t;
+    if (!bn_scale_shift(h, pre, c, s, t)) return false;
+    *s_out = upload(h, to_f32(s));
+    *t_out = upload(h, to_f32(t));
+    return true;
+}
+
+// E1: CAVE/BEAT_CVAE.py:334-388 (layers), :427-447 (sample)
+int pack_cvae3(egx_handle* h) {
+    BucketScope scope(h, "cvae3");
+    h->cvae3 = Cvae3W();
+    Cvae3W& c = h->cvae3;
+    Affine py, fus;
+    if (!linear_chain(h, "cvae3.Posterior_Y_embedding", {0, 2}, {8, 16, 32}, &py)) return 1;
+    if (!linear_chain(h, "cvae3.fusion_z_posterior", {0, 2}, {64, 128, 512}, &fus)) return 1;
+    c.w_y = upload(h, to_f32(py.W)); c.b_y = upload(h, to_f32(py.b));
+    c.w_f = upload(h, to_f32(fus.W)); c.b_f = upload(h, to_f32(fus.b));
+    const std::string d = "cvae3.Decoder.";
+    if (!upload_tensor(h, d + "0.weight", {4, 8, 3}, &c.t1_w) || !upload_tensor(h, d + "0.bias", {8}, &c.t1_b) ||
+        !upload_bn(h, d + "2", 8, &c.s1, &c.h1) ||
+        !upload_tensor(h, d + "3.weight", {8, 16, 3}, &c.t2_w) || !upload_tensor(h, d + "3.bias", {16}, &c.t2_b) ||
+        !upload_bn(h, d + "5", 16, &c.s2, &c.h2) ||
+        !upload_tensor(h, d + "6.weight", {32, 16, 3}, &c.c3_w) || !upload_tensor(h, d + "6.bias", {32}, &c.c3_b) ||
+        !upload_bn(h, d + "8", 32, &c.s3, &c.h3) ||
+        !upload_tensor(h, d + "9.weight", {60, 32, 3}, &c.c4_w) || !upload_tensor(h, d + "9.bias", {60}, &c.c4_b) ||
+        !upload_bn(h, d + "11", 60, &c.s4, &c.h4) ||
+        !upload_tensor(h, d + "12.weight", {60, 60, 3}, &c.c5_w) || !upload_tensor(h, d + "12.bias", {60}, &c.c5_b))
+        return 1;
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing cvae3 weights");
+    c.ready = true;
+    return 0;
+}
+
+// conv weight (cout, cin, k) with the following BatchNorm folded in: w' = s w, b' = s b + t
+bool upload_conv_bn(egx_handle* h, const std::string& conv, const std::string* bn, int cout, int cin, int k, float** w_out,
+                    float** b_out) {
+    const HostTensor *w, *b;
+    if (!need(h, conv + ".weight", {cout, cin, k}, &w) || !need(h, conv + ".bias", {cout}, &b)) return false;
+    std::vector<double> s(cout, 1.0), t(cout, 0.0);
+    if (bn && !bn_scale_shift(h, *bn, cout, s, t)) return false;
+    std::vector<float> wf(w->v.size()), bf(cout);
+    const size_t per = (size_t)cin * k;
+    for (int o = 0; o < cout; ++o) {
+        for (size_t i = 0; i < per; ++i) wf[o * per + i] = (float)(s[o] * (double)w->v[o * per + i]);
+        bf[o] = (float)(s[o] * (double)b->v[o] + t[o]);
+    }
+    *w_out = upload(h, wf);
+    *b_out = upload(h, bf);
+    return true;
+}
+
+// D1: PoseEncoderConv.  model/motion_ae.py:55-83 (out_net -> latent) / model/embedding_net.py:37-83 (out_net -> fc_mu)
+int pack_pose_enc(egx_handle* h, const std::string& family, const std::string& pre, bool with_fc_mu, PoseEncW* out) {
+    BucketScope scope(h, family);
+    *out = PoseEncW();
+    const HostTensor* w1 = find(h, pre + "net.0.0.weight");
+    const HostTensor* fc0 = find(h, pre + "out_net.0.weight");
+    const HostTensor* fc6 = find(h, pre + "out_net.6.weight");
+    if (!w1 || !fc0 || !fc6 || w1->shape.size() != 3 || fc0->shape.size() != 2 || fc6->shape.size() != 2) return 1;
+    const int P = (int)w1->shape[1], n_flat = (int)fc0->shape[1], L4 = n_flat / 32, L3 = L4 + 2, L2 = 2 * (L3 - 1) + 4, L = L2 + 4;
+    if (n_flat % 32 || L4 < 1) EGX_FAIL(h, "unexpected out_net.0 width for " + family);
+    const std::string bn0 = pre + "net.0.1", bn1 = pre + "net.1.1", bn2 = pre + "net.2.1";
+    if (!upload_conv_bn(h, pre + "net.0.0", &bn0, 32, P, 3, &out->w1, &out->b1) ||
+        !upload_conv_bn(h, pre + "net.1.0", &bn1, 64, 32, 3, &out->w2, &out->b2) ||
+        !upload_conv_bn(h, pre + "net.2.0", &bn2, 64, 64, 4, &out->w3, &out->b3) ||
+        !upload_conv_bn(h, pre + "net.3", nullptr, 32, 64, 3, &out->w4, &out->b4))
+        return 1;
+    // out_net: Linear BN LeakyReLU(True) Linear BN LeakyReLU(True) Linear; nn.LeakyReLU(True) sets negative_slope = 1.0,
+    // i.e. the identity (model/motion_ae.py:70,73; model/embedding_net.py:57,60), so the whole tail is affine
+    const int latent = (int)fc6->shape[0];
+    Affine a0, a3, a6;
+    std::vector<double> s, t;
+    if (!get_affine(h, pre + "out_net.0", n_flat, 256, &a0) || !bn_scale_shift(h, pre + "out_net.1", 256, s, t)) return 1;
+    scale_rows(a0, s, t);
+    if (!get_affine(h, pre + "out_net.3", 256, 128, &a3) || !bn_scale_shift(h, pre + "out_net.4", 128, s, t)) return 1;
+    scale_rows(a3, s, t);
+    if (!get_affine(h, pre + "out_net.6", 128, latent, &a6)) return 1;
+    Affine tail = compose(compose(a0, a3), a6);
+    if (with_fc_mu) {
+        Affine mu;
+        if (!get_affine(h, pre + "fc_mu", latent, 32, &mu)) return 1;
+        tail = compose(tail, mu);
+    }
+    out->w_fc = upload(h, to_f32(tail.W));
+    out->b_fc = upload(h, to_f32(tail.b));
+    out->L = L; out->P = P; out->n_out = tail.out;
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing " + family);
+    out->ready = true;
+    return 0;
+}
+
+// D1: per-frame MLP of model/FGD.py:30-41 (Encoder: Linear(282,512) Linear(512,512) Linear(512,512), Dropouts between)
+int pack_fgd_mlp(egx_handle* h) {
+    BucketScope scope(h, "fgd_mlp");
+    h->fgd_mlp = RowMlpW();
+    const HostTensor* w0 = find(h, "fgd_mlp.Encoder.0.weight");
+    if (!w0 || w0->shape.size() != 2) return 1;
+    const int in = (int)w0->shape[1], hid = (int)w0->shape[0];
+    Affine enc;
+    if (!linear_chain(h, "fgd_mlp.Encoder", {0, 2, 4}, {in, hid, hid, hid}, &enc)) return 1;
+    LinearW& l = h->fgd_mlp.lin;
+    l.in = in; l.out = hid;
+    const std::vector<float> wf = to_f32(enc.W);
+    l.w = upload(h, wf);
+    l.b = upload(h, to_f32(enc.b));
+    add_f16_copy(h, wf, hid, in, &l);
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing fgd_mlp");
+    h->fgd_mlp.ready = true;
+    return 0;
+}
+
+}  // namespace
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -733,6 +971,8 @@ void egx_destroy(egx_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->owned) cudaFree(p);
+    for (auto& kv : h->aux_owned)
+        for (void* p : kv.second) cudaFree(p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     delete h;
 }
@@ -757,6 +997,19 @@ int egx_set_weight(egx_handle* h, const char* key, const void* data, const int64
 int egx_finalize_weights(egx_handle* h) {
     if (!h) return 1;
     EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    // Pack every model family whose keys were staged since the last call (generator keys are un-prefixed,
+    // the small networks arrive under "cvae.", "cvae3.", "motion_ae.", "pose_enc.", "fgd_mlp.").
+    int packed = 0;
+    if (h->staged.count("cvae.Encoder.0.weight")) { if (pack_cvae(h)) return 1; ++packed; }
+    if (h->staged.count("cvae3.fusion_z_posterior.0.weight")) { if (pack_cvae3(h)) return 1; ++packed; }
+    if (h->staged.count("motion_ae.encoder.net.0.0.weight")) { if (pack_pose_enc(h, "motion_ae", "motion_ae.encoder.", false, &h->motion_ae)) return 1; ++packed; }
+    if (h->staged.count("pose_enc.net.0.0.weight")) { if (pack_pose_enc(h, "pose_enc", "pose_enc.", true, &h->pose_enc)) return 1; ++packed; }
+    if (h->staged.count("fgd_mlp.Encoder.0.weight")) { if (pack_fgd_mlp(h)) return 1; ++packed; }
+    if (!h->staged.count("audio_encoder.feat_extractor.conv1.weight")) {
+        if (!packed) EGX_FAIL(h, "no known weight family staged");
+        h->staged.clear();
+        return 0;
+    }
     // drop previously packed weights (keep the log-mel tables: first 6 allocations)
     for (size_t i = 6; i < h->owned.size(); ++i) cudaFree(h->owned[i]);
     h->owned.resize(6);
@@ -980,6 +1233,84 @@ int egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int di
     cudaStream_t s = (cudaStream_t)stream;
     StageScope sc(h, 8);
     LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, s));
+    return 0;
+}
+
+
+int egx_cvae_forward(egx_handle* h, const float* x, const float* y, const float* eps, int64_t n, float* out, float* mu,
+                     float* logvar, void* stream) {
+    if (!h) return 1;
+    if (!h->cvae.ready) EGX_FAIL(h, "cvae weights not loaded");
+    if (n == 0) return 0;
+    if (n < 0 || !x || !y || !eps || !out || !mu || !logvar) EGX_FAIL(h, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_cvae_mlp(h->cvae, x, y, eps, 0, n, out, mu, logvar, s));
+    return 0;
+}
+
+int egx_cvae_sample(egx_handle* h, const float* y, const float* z, int64_t n, float* out, void* stream) {
+    if (!h) return 1;
+    if (!h->cvae.ready) EGX_FAIL(h, "cvae weights not loaded");
+    if (n == 0) return 0;
+    if (n < 0 || !y || !z || !out) EGX_FAIL(h, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_cvae_mlp(h->cvae, nullptr, y, z, 1, n, out, nullptr, nullptr, s));
+    return 0;
+}
+
+int egx_cvae3_sample(egx_handle* h, const float* y, const float* z, int n, float* out, void* stream) {
+    if (!h) return 1;
+    if (!h->cvae3.ready) EGX_FAIL(h, "cvae3 weights not loaded");
+    if (n == 0) return 0;
+    if (n < 0 || !y || !z || !out) EGX_FAIL(h, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_cvae3_sample(h->cvae3, y, z, n, out, s));
+    return 0;
+}
+
+int egx_pose_features(egx_handle* h, int kind, const float* poses, int n_clips, int n_frames, int pose_dim, float* out,
+                      void* stream) {
+    if (!h) return 1;
+    if (kind != EGX_POSE_MOTION_AE && kind != EGX_POSE_EMBEDDING_NET) EGX_FAIL(h, "unknown pose feature net");
+    const PoseEncW& w = kind == EGX_POSE_MOTION_AE ? h->motion_ae : h->pose_enc;
+    if (!w.ready) EGX_FAIL(h, "pose feature net weights not loaded");
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || !poses || !out) EGX_FAIL(h, "null pointer argument");
+    if (n_frames != w.L || pose_dim != w.P)
+        EGX_FAIL(h, "pose clip shape (" + std::to_string(n_frames) + "," + std::to_string(pose_dim) + ") does not match the loaded net (" +
+                        std::to_string(w.L) + "," + std::to_string(w.P) + ")");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_pose_encoder(w, poses, n_clips, out, s));
+    return 0;
+}
+
+int egx_pose_feature_dim(const egx_handle* h, int kind) {
+    if (!h) return 0;
+    const PoseEncW& w = kind == EGX_POSE_MOTION_AE ? h->motion_ae : h->pose_enc;
+    return w.ready ? w.n_out : 0;
+}
+
+size_t egx_row_features_workspace(const egx_handle* h, int64_t n_rows) {
+    if (!h || !h->fgd_mlp.ready || n_rows <= 0) return 0;
+    return (size_t)n_rows * h->fgd_mlp.lin.ldw * sizeof(__half) + 256;
+}
+
+int egx_row_features(egx_handle* h, const float* rows, int64_t n_rows, int dim, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!h) return 1;
+    if (!h->fgd_mlp.ready) EGX_FAIL(h, "fgd_mlp weights not loaded");
+    if (n_rows == 0) return 0;
+    const LinearW& l = h->fgd_mlp.lin;
+    if (n_rows < 0 || !rows || !out || !workspace) EGX_FAIL(h, "null pointer argument");
+    if (dim != l.in) EGX_FAIL(h, "row width does not match the loaded net");
+    if (n_rows > (int64_t)0x7fffffff) EGX_FAIL(h, "too many rows for one call");
+    if (workspace_bytes < egx_row_features_workspace(h, n_rows)) EGX_FAIL(h, "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    __half* a16 = static_cast<__half*>(workspace);
+    LAUNCH(h, launch_cvt_pad_f16(rows, n_rows, l.in, l.in, a16, l.ldw, s));
+    GemmEpi e;
+    e.bias = l.b;
+    LAUNCH(h, launch_gemm_tc(a16, l.ldw, l.w16, l.ldw, (int)n_rows, l.out, l.in, e, out, l.out, nullptr, 0, s));
     return 0;
 }
 

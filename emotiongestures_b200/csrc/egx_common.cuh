@@ -79,6 +79,44 @@ struct Weights {
     std::vector<FFNW> enc_ffn, dec_ffn;
 };
 
+// ---- small networks either side of the generator (k_aux.cu); all pointers are device memory ----
+// C4  Full_model/BEAT_CVAE.py MLP_Reconstruct, Linear chains collapsed (eval: Dropout = identity)
+struct CvaeW {
+    float* w_x = nullptr;   // [90][64]  x -> (mu | logvar), k-major
+    float* b_x = nullptr;   // [64]
+    float* w_y = nullptr;   // [90][32]  y -> Posterior_Y_embedding
+    float* b_y = nullptr;   // [32]
+    float* w_d = nullptr;   // [64][92]  [z ; post_y] -> output (fusion_z_posterior + Decoder), 90 padded to 92
+    float* b_d = nullptr;   // [92]
+    bool ready = false;
+};
+// E1  CAVE/BEAT_CVAE.py MLP_Reconstruct_v3 (sampler half)
+struct Cvae3W {
+    float *w_y = nullptr, *b_y = nullptr;     // [32][8], [32]   Posterior_Y_embedding collapsed
+    float *w_f = nullptr, *b_f = nullptr;     // [512][64], [512] fusion_z_posterior collapsed
+    float *t1_w = nullptr, *t1_b = nullptr, *s1 = nullptr, *h1 = nullptr;   // ConvT 4->8 (cin,cout,3) + BN after LReLU
+    float *t2_w = nullptr, *t2_b = nullptr, *s2 = nullptr, *h2 = nullptr;   // ConvT 8->16
+    float *c3_w = nullptr, *c3_b = nullptr, *s3 = nullptr, *h3 = nullptr;   // Conv 16->32 (cout,cin,3)
+    float *c4_w = nullptr, *c4_b = nullptr, *s4 = nullptr, *h4 = nullptr;   // Conv 32->60
+    float *c5_w = nullptr, *c5_b = nullptr;                                 // Conv 60->60
+    bool ready = false;
+};
+// D1  PoseEncoderConv (model/motion_ae.py:55-62, model/embedding_net.py:67-83), BN folded, out_net collapsed
+struct PoseEncW {
+    int L = 0, P = 0, n_out = 0;
+    float *w1 = nullptr, *b1 = nullptr;       // (32,P,3)
+    float *w2 = nullptr, *b2 = nullptr;       // (64,32,3)
+    float *w3 = nullptr, *b3 = nullptr;       // (64,64,4), stride 2
+    float *w4 = nullptr, *b4 = nullptr;       // (32,64,3)
+    float *w_fc = nullptr, *b_fc = nullptr;   // [n_out][32*L4]
+    bool ready = false;
+};
+// D1  per-frame feature MLP (model/FGD.py:26-41 Encoder, three Linears collapsed into one)
+struct RowMlpW {
+    LinearW lin;                              // in -> out, fp16 copy for the tensor-core GEMM
+    bool ready = false;
+};
+
 // Log-mel tables (built in float64 on the host, stored as float32)
 struct LogmelTables {
     float* window = nullptr;      // [1024] periodic Hann
@@ -96,10 +134,16 @@ struct egx_handle {
     int device = 0;
     std::string err;
     std::map<std::string, egx::HostTensor> staged;   // weights as received
-    std::vector<void*> owned;                          // device allocations to free
+    std::vector<void*> owned;                          // device allocations to free (log-mel tables + generator)
+    std::map<std::string, std::vector<void*>> aux_owned;   // per aux-model family
+    std::vector<void*>* cur_bucket = nullptr;          // where upload() records allocations (null: `owned`)
     egx::Weights w;
     egx::LogmelTables lm;
-    bool finalized = false;
+    bool finalized = false;                            // generator weights packed
+    egx::CvaeW cvae;
+    egx::Cvae3W cvae3;
+    egx::PoseEncW motion_ae, pose_enc;
+    egx::RowMlpW fgd_mlp;
     int64_t launches = 0;
     // per-launch CUDA-event profiling (egx_profile_enable / egx_profile_read)
     bool profiling = false;
@@ -209,5 +253,11 @@ int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, 
 
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);
+
+// ---- k_aux.cu ----
+int launch_cvae_mlp(const CvaeW& w, const float* x, const float* y, const float* noise, int noise_is_z, int64_t n,
+                    float* out, float* mu, float* logvar, cudaStream_t s);
+int launch_cvae3_sample(const Cvae3W& w, const float* y, const float* z, int n, float* out, cudaStream_t s);
+int launch_pose_encoder(const PoseEncW& w, const float* poses, int B, float* out, cudaStream_t s);
 
 }  // namespace egx

@@ -112,6 +112,41 @@ EGX_API int  egx_debug_trunk(egx_handle* h, const float* spec, int n_clips, int 
 EGX_API int  egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int dim,
                         const double* shift, double* acc, void* stream);
 
+/* ---- small networks either side of the generator ------------------------------
+ * Their weights arrive through egx_set_weight under a family prefix followed by the module's own state_dict key:
+ *   "cvae."       Full_model/BEAT_CVAE.py   MLP_Reconstruct
+ *   "cvae3."      CAVE/BEAT_CVAE.py         MLP_Reconstruct_v3
+ *   "motion_ae."  model/motion_ae.py        MotionAE            (encoder half is used)
+ *   "pose_enc."   model/embedding_net.py    PoseEncoderConv
+ *   "fgd_mlp."    model/FGD.py              MLP_Reconstruct     (Encoder half is used)
+ * egx_finalize_weights packs whichever families were staged.  The reference draws its Gaussian noise inside the
+ * module (torch.randn / randn_like); here the caller passes the draw in, so results are reproducible and do not
+ * depend on how clips are sharded over GPUs. */
+
+/* Replaces: MLP_Reconstruct.forward (Full_model/BEAT_CVAE.py:98-114).  x, y (n,90); eps (n,32) is the randn_like
+ * draw of reparameterize (:91-94) -> out (n,90), mu (n,32), logvar (n,32). */
+EGX_API int  egx_cvae_forward(egx_handle* h, const float* x, const float* y, const float* eps, int64_t n,
+                      float* out, float* mu, float* logvar, void* stream);
+/* Replaces: MLP_Reconstruct.sample (Full_model/BEAT_CVAE.py:117-136).  y (n,90); z (n,32) is the torch.randn
+ * draw of :130 -> out (n,90). */
+EGX_API int  egx_cvae_sample(egx_handle* h, const float* y, const float* z, int64_t n, float* out, void* stream);
+/* Replaces: MLP_Reconstruct_v3.sample (CAVE/BEAT_CVAE.py:427-447).  y (n,8) one-hot emotion; z (n,32) the
+ * torch.randn draw of :441 -> out (n,60,512), the sampled_emotion_feature of the BEAT generator. */
+EGX_API int  egx_cvae3_sample(egx_handle* h, const float* y, const float* z, int n, float* out, void* stream);
+
+/* Replaces: the FGD feature nets of the evaluation loop (test_emotion_gesture_diversity_iterative.py:226-229).
+ * kind EGX_POSE_MOTION_AE:     MotionAE.encoder (model/motion_ae.py:55-83,125-130), poses (n,34,P) -> z (n,latent)
+ * kind EGX_POSE_EMBEDDING_NET: PoseEncoderConv.forward (model/embedding_net.py:67-83), poses (n,60,P) -> mu (n,32) */
+enum { EGX_POSE_MOTION_AE = 0, EGX_POSE_EMBEDDING_NET = 1 };
+EGX_API int  egx_pose_features(egx_handle* h, int kind, const float* poses, int n_clips, int n_frames,
+                       int pose_dim, float* out, void* stream);
+EGX_API int  egx_pose_feature_dim(const egx_handle* h, int kind);
+/* Replaces: MLP_Reconstruct.Encoder of model/FGD.py:30-41,66-82 applied per frame: rows (n,282) -> latent (n,512).
+ * workspace holds the fp16 copy of the rows (egx_row_features_workspace bytes). */
+EGX_API size_t egx_row_features_workspace(const egx_handle* h, int64_t n_rows);
+EGX_API int  egx_row_features(egx_handle* h, const float* rows, int64_t n_rows, int dim, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Parity probe of the tcgen05 Linear kernel alone: out = [relu](A W^T + bias) + addend, A (M,K), W (N,K),
  * out (M,N) f32; operands are rounded to fp16 inside.  Synchronises the stream (test-only). */
 EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias,

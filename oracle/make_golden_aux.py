@@ -1,0 +1,159 @@
+"""ORACLE tooling: pin oracle/aux_models.py against the REAL reference modules and write
+tests/golden/aux_*.npz.  Build container only (needs /root/reference):
+
+    python -m oracle.make_golden_aux
+
+For every small network of SURVEY.md §8 rows C4 / E1 / D1 it instantiates the reference class
+(stubbing the absent `fasttext` import of model/vocab.py), checks that the host mirror in
+emotiongestures_b200/aux_models.py has the same state_dict keys and shapes, loads the synthetic
+weights of oracle/synth.py into the reference, runs it with explicit noise (the reference's
+torch.randn calls are replayed by seeding and, where the draw happens on the CPU inside the
+module, by patching torch.randn for the duration of the call), asserts the restatement agrees
+to <= 2e-6 and stores seeds + reference outputs as small fixtures.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from emotiongestures_b200 import aux_models as mirrors  # noqa: E402
+from oracle import aux_models as oa  # noqa: E402
+from oracle import synth  # noqa: E402
+
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def rnd(shape, seed, tag):
+    return torch.from_numpy(np.random.default_rng([seed, tag]).standard_normal(shape).astype(np.float32))
+
+
+def same_layout(ref, mine):
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys()), (set(a) ^ set(b))
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+
+
+def rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+class patched_randn:
+    """Replay the module-internal torch.randn / randn_like draw with a tensor we control."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        self._randn, self._like = torch.randn, torch.randn_like
+        torch.randn = lambda *a, **k: self.value.clone()
+        torch.randn_like = lambda *a, **k: self.value.clone()
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._like
+
+
+def main():
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("fasttext", types.ModuleType("fasttext"))
+    sys.modules.setdefault("torch_dct", types.ModuleType("torch_dct"))
+    import importlib
+    out = {}
+
+    # ---- C4: Full_model/BEAT_CVAE.py MLP_Reconstruct --------------------------------------------------
+    ref = importlib.import_module("Full_model.BEAT_CVAE").MLP_Reconstruct().eval()
+    mine = mirrors.MLP_Reconstruct()
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 11)
+    ref.load_state_dict(sd)
+    n = 37
+    x, y, eps = rnd((n, 90), 11, 1), rnd((n, 90), 11, 2), rnd((n, 32), 11, 3)
+    with torch.no_grad(), patched_randn(eps):
+        r_out, r_mu, r_lv = ref(x, y)
+        r_smp = ref.sample(y)
+    with torch.no_grad():
+        o_out, o_mu, o_lv = oa.cvae_forward(sd, x, y, eps)
+        o_smp = oa.cvae_decode(sd, y, eps)
+    for nm, a, b in (("out", o_out, r_out), ("mu", o_mu, r_mu), ("logvar", o_lv, r_lv), ("sample", o_smp, r_smp)):
+        print(f"  cvae {nm}: oracle vs reference {rel(a, b):.2e}")
+        assert rel(a, b) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_cvae.npz"), seed=11, n=n, out=r_out.numpy(), mu=r_mu.numpy(),
+                        logvar=r_lv.numpy(), sample=r_smp.numpy())
+
+    # ---- E1: CAVE/BEAT_CVAE.py MLP_Reconstruct_v3.sample ----------------------------------------------
+    ref = importlib.import_module("CAVE.BEAT_CVAE").MLP_Reconstruct_v3().eval()
+    mine = mirrors.MLP_Reconstruct_v3()
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 12)
+    ref.load_state_dict(sd)
+    n = 3
+    lab = torch.tensor([1, 7, 4])
+    y = torch.nn.functional.one_hot(lab, 8).float()
+    z = rnd((n, 32), 12, 1)
+    with torch.no_grad(), patched_randn(z):
+        r = ref.sample(y)
+    with torch.no_grad():
+        o = oa.cvae3_sample(sd, y, z)
+    print(f"  cvae3 sample: oracle vs reference {rel(o, r):.2e}", tuple(r.shape))
+    assert rel(o, r) <= 2e-6 and tuple(r.shape) == (n, 60, 512)
+    np.savez_compressed(os.path.join(GOLD, "aux_cvae3.npz"), seed=12, labels=lab.numpy(), sample=r.numpy().astype(np.float32))
+
+    # ---- D1: MotionAE.encoder (TED) ------------------------------------------------------------------
+    ref = importlib.import_module("model.motion_ae").MotionAE(126, 128).eval()
+    mine = mirrors.MotionAE(126, 128)
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 13)
+    ref.load_state_dict(sd)
+    n = 5
+    poses = rnd((n, 34, 126), 13, 1)
+    with torch.no_grad():
+        _, r = ref(poses)
+        o = oa.pose_encoder(sd, poses, "encoder.")
+    print(f"  motion_ae z: oracle vs reference {rel(o, r):.2e}", tuple(r.shape))
+    assert rel(o, r) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_motion_ae.npz"), seed=13, n=n, z=r.numpy())
+
+    # ---- D1: embedding_net.PoseEncoderConv (BEAT) ------------------------------------------------------
+    ref = importlib.import_module("model.embedding_net").PoseEncoderConv(60, 282).eval()
+    mine = mirrors.PoseEncoderConv(60, 282)
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 14)
+    ref.load_state_dict(sd)
+    n = 4
+    poses = rnd((n, 60, 282), 14, 1)
+    with torch.no_grad():
+        _, r, _ = ref(poses, False)
+        o = oa.pose_encoder(sd, poses, "", fc_mu=True)
+    print(f"  pose_enc mu: oracle vs reference {rel(o, r):.2e}", tuple(r.shape))
+    assert rel(o, r) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_pose_enc.npz"), seed=14, n=n, mu=r.numpy())
+
+    # ---- D1: model/FGD.py MLP_Reconstruct latent -------------------------------------------------------
+    ref = importlib.import_module("model.FGD").MLP_Reconstruct().eval()
+    mine = mirrors.FGDNet()
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 15)
+    ref.load_state_dict(sd)
+    n = 2
+    poses = rnd((n, 60, 282), 15, 1)
+    with torch.no_grad():
+        _, r = ref(poses)
+        o = oa.fgd_latent(sd, poses)
+    print(f"  fgd latent: oracle vs reference {rel(o, r):.2e}", tuple(r.shape))
+    assert rel(o, r) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_fgd_mlp.npz"), seed=15, n=n, latent=r.numpy())
+    return out
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    main()
+    for f in sorted(os.listdir(GOLD)):
+        if f.startswith("aux_"):
+            print(f"  {f}: {os.path.getsize(os.path.join(GOLD, f)) / 1024:.0f} KiB")

@@ -26,12 +26,12 @@ def _rng(key: str, seed: int) -> np.random.Generator:
     return np.random.default_rng([seed, zlib.crc32(_canonical(key).encode())])
 
 
-def synth_tensor(key: str, shape, seed: int, dtype=torch.float32) -> torch.Tensor:
+def synth_tensor(key: str, shape, seed: int, dtype=torch.float32, norm: bool = False) -> torch.Tensor:
     r = _rng(key, seed)
     shape = tuple(shape)
     if key.endswith("num_batches_tracked"):
         return torch.zeros((), dtype=torch.int64)
-    is_norm = any(m in key for m in _NORM_MARKERS)
+    is_norm = norm or any(m in key for m in _NORM_MARKERS)
     if key.endswith("running_var"):
         a = r.uniform(0.5, 1.5, shape)
     elif key.endswith("running_mean"):
@@ -60,7 +60,9 @@ def synth_state_dict(template: dict, seed: int = 0) -> dict:
         if "pos_table" in k:
             out[k] = v.clone()
         else:
-            out[k] = synth_tensor(k, v.shape, seed)
+            # a parameter whose module also owns a running_mean is a BatchNorm weight / bias
+            norm = (k.rsplit(".", 1)[0] + ".running_mean") in template
+            out[k] = synth_tensor(k, v.shape, seed, norm=norm)
     return out
 
 

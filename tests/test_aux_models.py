@@ -1,0 +1,167 @@
+"""Small networks either side of the generator.
+
+CPU part: the oracle restatement (oracle/aux_models.py) reproduces the outputs the REAL reference
+modules produced for the same synthetic weights and inputs (tests/golden/aux_*.npz, written by
+oracle/make_golden_aux.py), and the host mirrors keep the reference's state_dict layout.
+GPU part (-m gpu): the CUDA path through the C ABI against those reference outputs.
+
+Tolerances.  The CUDA kernels compute in fp32 but fold eval-mode algebra on the host in fp64
+(Linear chains without activations collapse, BatchNorm becomes scale/shift), so they differ from
+the reference's fp32 chain only by rounding order: gate 2e-5 relative to the output scale.  The
+per-frame FGD MLP runs on the fp16 tensor-core GEMM: gate 2e-3 (the bf16-path tolerance of the
+north star)."""
+import numpy as np
+import pytest
+import torch
+
+from emotiongestures_b200 import aux_models as mirrors
+from oracle import aux_models as oa
+from oracle import synth
+from tests.helpers import load_golden, rel_max
+
+
+def rnd(shape, seed, tag):
+    return torch.from_numpy(np.random.default_rng([seed, tag]).standard_normal(shape).astype(np.float32))
+
+
+def build(cls, seed, *args):
+    m = cls(*args).eval()
+    sd = synth.synth_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+CASES = {
+    "cvae": (mirrors.MLP_Reconstruct, 11, ()),
+    "cvae3": (mirrors.MLP_Reconstruct_v3, 12, ()),
+    "motion_ae": (mirrors.MotionAE, 13, (126, 128)),
+    "pose_enc": (mirrors.PoseEncoderConv, 14, (60, 282)),
+    "fgd_mlp": (mirrors.FGDNet, 15, ()),
+}
+
+
+def reference_and_inputs(name):
+    g = load_golden("aux_" + name)
+    cls, seed, args = CASES[name]
+    m, sd = build(cls, seed, *args)
+    if name == "cvae":
+        n = int(g["n"])
+        ins = dict(x=rnd((n, 90), seed, 1), y=rnd((n, 90), seed, 2), eps=rnd((n, 32), seed, 3))
+        ref = {k: torch.from_numpy(g[k]) for k in ("out", "mu", "logvar", "sample")}
+    elif name == "cvae3":
+        lab = torch.from_numpy(g["labels"])
+        ins = dict(y=torch.nn.functional.one_hot(lab, 8).float(), z=rnd((len(lab), 32), seed, 1))
+        ref = {"sample": torch.from_numpy(g["sample"])}
+    elif name == "motion_ae":
+        ins = dict(poses=rnd((int(g["n"]), 34, 126), seed, 1))
+        ref = {"z": torch.from_numpy(g["z"])}
+    elif name == "pose_enc":
+        ins = dict(poses=rnd((int(g["n"]), 60, 282), seed, 1))
+        ref = {"mu": torch.from_numpy(g["mu"])}
+    else:
+        ins = dict(poses=rnd((int(g["n"]), 60, 282), seed, 1))
+        ref = {"latent": torch.from_numpy(g["latent"])}
+    return m, sd, ins, ref
+
+
+def oracle_outputs(name, sd, ins):
+    with torch.no_grad():
+        if name == "cvae":
+            out, mu, lv = oa.cvae_forward(sd, ins["x"], ins["y"], ins["eps"])
+            return {"out": out, "mu": mu, "logvar": lv, "sample": oa.cvae_decode(sd, ins["y"], ins["eps"])}
+        if name == "cvae3":
+            return {"sample": oa.cvae3_sample(sd, ins["y"], ins["z"])}
+        if name == "motion_ae":
+            return {"z": oa.pose_encoder(sd, ins["poses"], "encoder.")}
+        if name == "pose_enc":
+            return {"mu": oa.pose_encoder(sd, ins["poses"], "", fc_mu=True)}
+        return {"latent": oa.fgd_latent(sd, ins["poses"])}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_golden(name):
+    _, sd, ins, ref = reference_and_inputs(name)
+    got = oracle_outputs(name, sd, ins)
+    for k, r in ref.items():
+        assert got[k].shape == r.shape
+        assert rel_max(got[k], r) <= 2e-6, (name, k)
+
+
+def test_mirrors_refuse_cpu_and_training_mode():
+    m, _ = build(mirrors.MLP_Reconstruct, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.sample(torch.zeros(2, 90))
+    m3, _ = build(mirrors.MLP_Reconstruct_v3, 1)
+    with pytest.raises(RuntimeError, match="training-side"):
+        m3(torch.zeros(1, 60, 512), torch.zeros(1, 8))
+
+
+def test_pose_encoder_lengths_follow_the_reference():
+    with pytest.raises(ValueError):
+        mirrors.PoseEncoderConv(34, 126)         # embedding_net's out_net.0 is 800 wide: 60 frames only
+    with pytest.raises(ValueError):
+        mirrors.MotionAEEncoder(60, 126, 128)    # motion_ae's is 384 wide: 34 frames only
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU parity through the C ABI
+# ------------------------------------------------------------------------------------------------
+def device_outputs(name, m, ins):
+    m = m.cuda()
+    d = {k: v.cuda() for k, v in ins.items()}
+    with torch.no_grad():
+        if name == "cvae":
+            out, mu, lv = m(d["x"], d["y"], eps=d["eps"])
+            return {"out": out, "mu": mu, "logvar": lv, "sample": m.sample(d["y"], z=d["eps"])}
+        if name == "cvae3":
+            return {"sample": m.sample(d["y"], z=d["z"])}
+        if name == "motion_ae":
+            return {"z": m(d["poses"])[1]}
+        if name == "pose_enc":
+            return {"mu": m(d["poses"], False)[1]}
+        return {"latent": m(d["poses"])[1]}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_reference_golden(name):
+    m, _, ins, ref = reference_and_inputs(name)
+    got = device_outputs(name, m, ins)
+    tol = 2e-3 if name == "fgd_mlp" else 2e-5
+    for k, r in ref.items():
+        g = got[k].cpu()
+        assert g.shape == r.shape and not torch.isnan(g).any()
+        assert rel_max(g, r) <= tol, (name, k, rel_max(g, r))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n", [("cvae", 1), ("cvae", 1000), ("motion_ae", 300), ("pose_enc", 150), ("cvae3", 150),
+                                    ("fgd_mlp", 77)])
+def test_cuda_matches_oracle_at_ragged_sizes(name, n):
+    """Sizes that do not divide the kernels' tiles / exceed one wave, against the oracle on the same inputs."""
+    cls, seed, args = CASES[name]
+    m, sd = build(cls, seed + 100, *args)
+    if name == "cvae":
+        ins = dict(x=rnd((n, 90), n, 1), y=rnd((n, 90), n, 2), eps=rnd((n, 32), n, 3))
+    elif name == "cvae3":
+        ins = dict(y=torch.nn.functional.one_hot(torch.arange(n) % 8, 8).float(), z=rnd((n, 32), n, 1))
+    elif name == "motion_ae":
+        ins = dict(poses=rnd((n, 34, 126), n, 1))
+    else:
+        ins = dict(poses=rnd((n, 60, 282), n, 1))
+    ref = oracle_outputs(name, oa.cast(sd, torch.float64), {k: v.double() for k, v in ins.items()})
+    got = device_outputs(name, m, ins)
+    tol = 2e-3 if name == "fgd_mlp" else 2e-5
+    for k, r in ref.items():
+        assert rel_max(got[k].cpu(), r) <= tol, (name, k, rel_max(got[k].cpu(), r))
+
+
+@pytest.mark.gpu
+def test_cuda_empty_batches_and_shape_errors():
+    m, _ = build(mirrors.MLP_Reconstruct, 3)
+    m = m.cuda()
+    assert m.sample(torch.zeros(0, 90, device="cuda")).shape == (0, 90)
+    enc, _ = build(mirrors.MotionAE, 3, 126, 128)
+    enc = enc.cuda()
+    with pytest.raises(RuntimeError, match="does not match"):
+        enc(torch.zeros(2, 60, 126, device="cuda"))
