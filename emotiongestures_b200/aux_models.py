@@ -164,6 +164,39 @@ class FGDNet(_DeviceModule):
         return None, out.view(*lead, hidden)
 
 
+class EmotionNet(_DeviceModule):
+    """model/audio_emotion_classifer.py:17-49 — the audio emotion classifier (row C3): a four-stage
+    SE-ResNet ([3,4,6,3] blocks, 32..256 filters; model/emotion_ResNetSE34V2.py) over a (B,128,124)
+    log-mel, then Linear+ReLU x5 and ``last_fc``.  Returns logits (the reference leaves ``acn`` off)."""
+
+    _family = "emotion_net."
+
+    def __init__(self):
+        super().__init__()
+        from .generator import _Trunk
+        self.emotion_encoder = _Trunk(layers=(3, 4, 6, 3), filters=(32, 64, 128, 256))
+        dims = [256 * 16 * 16, 4096, 2048, 512, 128, 64]
+        mods = []
+        for i in range(5):
+            mods += [nn.Linear(dims[i], dims[i + 1]), nn.ReLU(True)]
+        self.emotion_eocder_fc = nn.Sequential(*mods)
+        self.last_fc = nn.Linear(64, 8)
+        self.acn = nn.Softmax(dim=1)
+
+    def forward(self, mfcc):
+        eng = self._engine()
+        x = eng._f32(mfcc, "mfcc")
+        if x.dim() != 3:
+            raise RuntimeError("mfcc must be (B, n_mels, W)")
+        b, n_mels, w = x.shape
+        logits = torch.empty((b, 8), device=eng.device)
+        ws = torch.empty(int(eng.lib.egx_emotion_net_workspace(eng._h, b, n_mels, w)), dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            eng._check(eng.lib.egx_emotion_net_forward(eng._h, _ptr(x), b, n_mels, w, _ptr(logits), _ptr(ws), ws.numel(),
+                                                       eng._stream()), "egx_emotion_net_forward")
+        return logits
+
+
 def _conv_norm_relu(cin, cout, downsample=False):
     k, s = (4, 2) if downsample else (3, 1)
     return nn.Sequential(nn.Conv1d(cin, cout, kernel_size=k, stride=s), nn.BatchNorm1d(cout), nn.LeakyReLU(0.2, True))
@@ -258,4 +291,4 @@ class PoseEncoderConv(_PoseEncoderBase):
         return mu, mu, None
 
 
-__all__ = ["MLP_Reconstruct", "MLP_Reconstruct_v3", "FGDNet", "MotionAE", "MotionAEEncoder", "PoseEncoderConv"]
+__all__ = ["MLP_Reconstruct", "MLP_Reconstruct_v3", "FGDNet", "EmotionNet", "MotionAE", "MotionAEEncoder", "PoseEncoderConv"]

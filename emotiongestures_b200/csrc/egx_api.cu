@@ -159,6 +159,40 @@ bool make_ffn(egx_handle* h, const std::string& pre, const egx_cfg& c, FFNW* f) 
            make_ln(h, pre + ".layer_norm", c.d_model, &f->ln);
 }
 
+// SE-ResNet trunk under `fe` (Full_model/ResNetSE34V2.py:13-55; model/emotion_ResNetSE34V2.py adds layer4):
+// stem conv+ReLU+BN, then n_layers stages of SEBasicBlocks, filters 32 << stage, depths [3,4,6,3].
+bool pack_trunk(egx_handle* h, const std::string& fe, int n_layers, ConvW* stem, std::vector<BlockW>* blocks) {
+    {
+        const std::string bk = fe + ".conv1.bias";
+        if (!make_conv(h, fe + ".conv1.weight", &bk, fe + ".bn1", 1, 32, 3, 1, 1, stem)) return false;
+    }
+    static const int nblk[4] = {3, 4, 6, 3};
+    int cin = 32;
+    for (int li = 0; li < n_layers; ++li)
+        for (int b = 0; b < nblk[li]; ++b) {
+            const std::string pre = fe + ".layer" + std::to_string(li + 1) + "." + std::to_string(b);
+            const int cout = 32 << li, stride = (b == 0 && li > 0) ? 2 : 1;
+            BlockW bw;
+            if (!make_conv(h, pre + ".conv1.weight", nullptr, pre + ".bn1", cin, cout, 3, stride, 1, &bw.conv1)) return false;
+            if (!make_conv(h, pre + ".conv2.weight", nullptr, pre + ".bn2", cout, cout, 3, 1, 0, &bw.conv2)) return false;
+            bw.has_down = (stride != 1 || cin != cout);
+            if (bw.has_down &&
+                !make_conv(h, pre + ".downsample.0.weight", nullptr, pre + ".downsample.1", cin, cout, 1, stride, 0, &bw.down))
+                return false;
+            const int r = cout / 8;
+            const HostTensor *w1, *b1, *w2, *b2;
+            if (!need(h, pre + ".se.fc.0.weight", {r, cout}, &w1) || !need(h, pre + ".se.fc.0.bias", {r}, &b1) ||
+                !need(h, pre + ".se.fc.2.weight", {cout, r}, &w2) || !need(h, pre + ".se.fc.2.bias", {cout}, &b2))
+                return false;
+            bw.se.c = cout; bw.se.r = r;
+            bw.se.w1 = upload(h, w1->v); bw.se.b1 = upload(h, b1->v);
+            bw.se.w2 = upload(h, w2->v); bw.se.b2 = upload(h, b2->v);
+            blocks->push_back(bw);
+            cin = cout;
+        }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // log-mel tables (float64 on the host)
 // ---------------------------------------------------------------------------------------------
@@ -540,42 +574,57 @@ int linear_tc(egx_handle* h, const LinearW& w, const __half* A, int lda, int M, 
     return 0;
 }
 
-int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto, __half** result, cudaStream_t s) {
-    __half *x = sl.act[0], *y = sl.act[1], *z = sl.act[2];
+// Trunk on the tensor-core arm over caller-provided buffers: act[3] hold (B, H0, W0, 32) fp16 maps, `down` a
+// (B, H0/2, W0/2, 64) one; returns the buffer and geometry of stage `upto` (0 stem, 1.. layers).
+struct TrunkBufs {
+    __half *act[3], *down;
+    float* se_sums;
+};
+
+int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& blocks, int n_layers, int H0, int W0,
+                 const float* spec, int B, const TrunkBufs& tb, int upto, __half** result, int* Hout, int* Wout,
+                 cudaStream_t s) {
+    __half *x = tb.act[0], *y = tb.act[1], *z = tb.act[2];
     {
         StageScope sc(h, 2);
-        LAUNCH(h, launch_stem<__half>(h->w.stem, spec, B, h->H[0], h->W[0], x, s));
+        LAUNCH(h, launch_stem<__half>(stem, spec, B, H0, W0, x, s));
     }
-    *result = x;
+    *result = x; *Hout = H0; *Wout = W0;
     if (upto == 0) return 0;
-    static const int nblk[3] = {3, 4, 6};
+    static const int nblk[4] = {3, 4, 6, 3};
     int bi = 0;
-    int Hc = h->H[0], Wc = h->W[0];
-    for (int li = 0; li < 3; ++li) {
+    int Hc = H0, Wc = W0;
+    for (int li = 0; li < n_layers; ++li) {
+        const int Ho = li ? (Hc + 1) / 2 : Hc, Wo = li ? (Wc + 1) / 2 : Wc;
         for (int b = 0; b < nblk[li]; ++b, ++bi) {
-            const BlockW& bw = h->w.blocks[bi];
-            const int Ho = h->H[li], Wo = h->W[li];
+            const BlockW& bw = blocks[bi];
             const __half* res = x;
             {
                 StageScope sc(h, 3);
                 LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, nullptr, s));
                 // conv2's epilogue also emits the per-tile channel sums the SE gate averages
-                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, sl.se_sums, s));
+                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, tb.se_sums, s));
                 if (bw.has_down) {
-                    LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, sl.down, 0, nullptr, s));
-                    res = sl.down;
+                    LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, tb.down, 0, nullptr, s));
+                    res = tb.down;
                 }
             }
             StageScope sc(h, 4);
-            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, sl.se_sums, conv_tc_tiles_per_clip(bw.conv2.cin, bw.conv2.cout, Ho, Wo), B, Ho * Wo, y,
+            LAUNCH(h, launch_se_apply<__half>(bw.se, z, res, tb.se_sums, conv_tc_tiles_per_clip(bw.conv2.cin, bw.conv2.cout, Ho, Wo), B, Ho * Wo, y,
                                               s));
             std::swap(x, y);
             Hc = Ho; Wc = Wo;
         }
-        *result = x;
+        *result = x; *Hout = Hc; *Wout = Wc;
         if (upto == li + 1) return 0;
     }
     return 0;
+}
+
+int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto, __half** result, cudaStream_t s) {
+    TrunkBufs tb{{sl.act[0], sl.act[1], sl.act[2]}, sl.down, sl.se_sums};
+    int Ho, Wo;
+    return run_trunk_tc(h, h->w.stem, h->w.blocks, 3, h->H[0], h->W[0], spec, B, tb, upto, result, &Ho, &Wo, s);
 }
 
 int forward_tc(egx_handle* h, const float* spec, const float* prior, const float* sampled, int B, float* poses,
@@ -908,6 +957,59 @@ int pack_pose_enc(egx_handle* h, const std::string& family, const std::string& p
     return 0;
 }
 
+
+// C3: model/audio_emotion_classifer.py:17-49 — ResNetSE [3,4,6,3] x [32,64,128,256] + six Linears.
+// The first Linear reads the reference's NCHW flatten (c, h, w); our maps are NHWC, so its columns are permuted
+// once here and the layer-4 map is the GEMM's A operand as it lies in memory.
+int pack_emotion_net(egx_handle* h) {
+    BucketScope scope(h, "emotion_net");
+    h->emo = EmotionNetW();
+    EmotionNetW& e = h->emo;
+    if (!pack_trunk(h, "emotion_net.emotion_encoder", 4, &e.stem, &e.blocks)) return 1;
+    const HostTensor* w0 = find(h, "emotion_net.emotion_eocder_fc.0.weight");
+    if (!w0 || w0->shape.size() != 2 || w0->shape[1] % 256) EGX_FAIL(h, "emotion_net: unexpected first Linear");
+    const int flat = (int)w0->shape[1], hw = flat / 256;
+    const int dims[7] = {flat, 4096, 2048, 512, 128, 64, 8};
+    for (int i = 0; i < 6; ++i) {
+        const std::string pre = i < 5 ? "emotion_net.emotion_eocder_fc." + std::to_string(2 * i) : std::string("emotion_net.last_fc");
+        const HostTensor *w, *b;
+        if (!need(h, pre + ".weight", {dims[i + 1], dims[i]}, &w) || !need(h, pre + ".bias", {dims[i + 1]}, &b)) return 1;
+        LinearW& l = e.fc[i];
+        l.in = dims[i]; l.out = dims[i + 1]; l.ldw = dims[i]; l.w = nullptr;
+        std::vector<__half> w16((size_t)l.out * l.in);
+        if (i == 0) {
+            for (int o = 0; o < l.out; ++o)
+                for (int c = 0; c < 256; ++c)
+                    for (int p = 0; p < hw; ++p)
+                        w16[(size_t)o * flat + (size_t)p * 256 + c] = __float2half_rn(w->v[(size_t)o * flat + (size_t)c * hw + p]);
+        } else {
+            for (size_t j = 0; j < w16.size(); ++j) w16[j] = __float2half_rn(w->v[j]);
+        }
+        l.w16 = upload(h, w16);
+        l.b = upload(h, b->v);
+    }
+    e.flat = flat;
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing emotion_net");
+    e.ready = true;
+    return 0;
+}
+
+struct EmoSlots {
+    TrunkBufs tb;
+    __half* fc[5];
+};
+
+EmoSlots plan_emotion(int B, int H0, int W0, Plan& p) {
+    EmoSlots s;
+    const size_t map1 = (size_t)B * H0 * W0 * 32;
+    for (auto& a : s.tb.act) a = p.take<__half>(map1);
+    s.tb.down = p.take<__half>((size_t)B * ((H0 + 1) / 2) * ((W0 + 1) / 2) * 64);
+    s.tb.se_sums = p.take<float>((size_t)B * (size_t)(H0 * W0 / 64 + 8) * 32);
+    static const int dims[5] = {4096, 2048, 512, 128, 64};
+    for (int i = 0; i < 5; ++i) s.fc[i] = p.take<__half>((size_t)B * dims[i]);
+    return s;
+}
+
 // D1: per-frame MLP of model/FGD.py:30-41 (Encoder: Linear(282,512) Linear(512,512) Linear(512,512), Dropouts between)
 int pack_fgd_mlp(egx_handle* h) {
     BucketScope scope(h, "fgd_mlp");
@@ -1005,6 +1107,7 @@ int egx_finalize_weights(egx_handle* h) {
     if (h->staged.count("motion_ae.encoder.net.0.0.weight")) { if (pack_pose_enc(h, "motion_ae", "motion_ae.encoder.", false, &h->motion_ae)) return 1; ++packed; }
     if (h->staged.count("pose_enc.net.0.0.weight")) { if (pack_pose_enc(h, "pose_enc", "pose_enc.", true, &h->pose_enc)) return 1; ++packed; }
     if (h->staged.count("fgd_mlp.Encoder.0.weight")) { if (pack_fgd_mlp(h)) return 1; ++packed; }
+    if (h->staged.count("emotion_net.emotion_encoder.conv1.weight")) { if (pack_emotion_net(h)) return 1; ++packed; }
     if (!h->staged.count("audio_encoder.feat_extractor.conv1.weight")) {
         if (!packed) EGX_FAIL(h, "no known weight family staged");
         h->staged.clear();
@@ -1016,35 +1119,7 @@ int egx_finalize_weights(egx_handle* h) {
     h->w = Weights();
     const egx_cfg& c = h->cfg;
     Weights& w = h->w;
-    const std::string fe = "audio_encoder.feat_extractor";
-    {
-        const std::string bk = fe + ".conv1.bias";
-        if (!make_conv(h, fe + ".conv1.weight", &bk, fe + ".bn1", 1, 32, 3, 1, 1, &w.stem)) return 1;
-    }
-    static const int nblk[3] = {3, 4, 6}, filt[3] = {32, 64, 128};
-    int cin = 32;
-    for (int li = 0; li < 3; ++li)
-        for (int b = 0; b < nblk[li]; ++b) {
-            const std::string pre = fe + ".layer" + std::to_string(li + 1) + "." + std::to_string(b);
-            const int cout = filt[li], stride = (b == 0 && li > 0) ? 2 : 1;
-            BlockW bw;
-            if (!make_conv(h, pre + ".conv1.weight", nullptr, pre + ".bn1", cin, cout, 3, stride, 1, &bw.conv1)) return 1;
-            if (!make_conv(h, pre + ".conv2.weight", nullptr, pre + ".bn2", cout, cout, 3, 1, 0, &bw.conv2)) return 1;
-            bw.has_down = (stride != 1 || cin != cout);
-            if (bw.has_down &&
-                !make_conv(h, pre + ".downsample.0.weight", nullptr, pre + ".downsample.1", cin, cout, 1, stride, 0, &bw.down))
-                return 1;
-            const int r = cout / 8;
-            const HostTensor *w1, *b1, *w2, *b2;
-            if (!need(h, pre + ".se.fc.0.weight", {r, cout}, &w1) || !need(h, pre + ".se.fc.0.bias", {r}, &b1) ||
-                !need(h, pre + ".se.fc.2.weight", {cout, r}, &w2) || !need(h, pre + ".se.fc.2.bias", {cout}, &b2))
-                return 1;
-            bw.se.c = cout; bw.se.r = r;
-            bw.se.w1 = upload(h, w1->v); bw.se.b1 = upload(h, b1->v);
-            bw.se.w2 = upload(h, w2->v); bw.se.b2 = upload(h, b2->v);
-            w.blocks.push_back(bw);
-            cin = cout;
-        }
+    if (!pack_trunk(h, "audio_encoder.feat_extractor", 3, &w.stem, &w.blocks)) return 1;
     {
         const std::string bk = "audio_encoder.final_conv1.bias";
         if (!make_conv(h, "audio_encoder.final_conv1.weight", &bk, "audio_encoder.bn1", 128, c.frames, 3, 1, 0, &w.final_conv))
@@ -1311,6 +1386,45 @@ int egx_row_features(egx_handle* h, const float* rows, int64_t n_rows, int dim, 
     GemmEpi e;
     e.bias = l.b;
     LAUNCH(h, launch_gemm_tc(a16, l.ldw, l.w16, l.ldw, (int)n_rows, l.out, l.in, e, out, l.out, nullptr, 0, s));
+    return 0;
+}
+
+
+size_t egx_emotion_net_workspace(const egx_handle* h, int n_clips, int n_mels, int n_cols) {
+    if (!h || n_clips <= 0) return 0;
+    Plan p;
+    plan_emotion(n_clips, n_mels, n_cols, p);
+    return p.off + 256;
+}
+
+int egx_emotion_net_forward(egx_handle* h, const float* spec, int n_clips, int n_mels, int n_cols, float* logits,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return 1;
+    if (!h->emo.ready) EGX_FAIL(h, "emotion_net weights not loaded");
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || !spec || !logits || !workspace) EGX_FAIL(h, "null pointer argument");
+    const EmotionNetW& e = h->emo;
+    int Hc = n_mels, Wc = n_cols;
+    for (int i = 0; i < 3; ++i) { Hc = (Hc + 1) / 2; Wc = (Wc + 1) / 2; }
+    if (n_cols % 2 || Hc * Wc * 256 != e.flat)
+        EGX_FAIL(h, "spectrogram (" + std::to_string(n_mels) + "," + std::to_string(n_cols) + ") does not flatten to the " +
+                        std::to_string(e.flat) + " inputs of emotion_eocder_fc.0");
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan p;
+    p.base = static_cast<char*>(workspace);
+    EmoSlots sl = plan_emotion(n_clips, n_mels, n_cols, p);
+    if (p.off > workspace_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
+    __half* feat = nullptr;
+    int Ho, Wo;
+    if (run_trunk_tc(h, e.stem, e.blocks, 4, n_mels, n_cols, spec, n_clips, sl.tb, 4, &feat, &Ho, &Wo, s)) return 1;
+    StageScope sc(h, 5);
+    const __half* a = feat;
+    for (int i = 0; i < 6; ++i) {
+        const LinearW& l = e.fc[i];
+        if (linear_tc(h, l, a, l.in, n_clips, i == 5 ? logits : nullptr, 8, i < 5 ? sl.fc[i] : nullptr, l.out, i < 5, nullptr, 0, s))
+            return 1;
+        if (i < 5) a = sl.fc[i];
+    }
     return 0;
 }
 

@@ -117,6 +117,15 @@ struct RowMlpW {
     bool ready = false;
 };
 
+// C3  model/audio_emotion_classifer.py EmotionNet: four-stage SE-ResNet + six Linears (fp16 tensor-core arm only)
+struct EmotionNetW {
+    ConvW stem;
+    std::vector<BlockW> blocks;     // 3 + 4 + 6 + 3
+    LinearW fc[6];                  // 65536->4096->2048->512->128->64->8; fc[0] columns permuted to NHWC order
+    int flat = 0;
+    bool ready = false;
+};
+
 // Log-mel tables (built in float64 on the host, stored as float32)
 struct LogmelTables {
     float* window = nullptr;      // [1024] periodic Hann
@@ -144,6 +153,7 @@ struct egx_handle {
     egx::Cvae3W cvae3;
     egx::PoseEncW motion_ae, pose_enc;
     egx::RowMlpW fgd_mlp;
+    egx::EmotionNetW emo;
     int64_t launches = 0;
     // per-launch CUDA-event profiling (egx_profile_enable / egx_profile_read)
     bool profiling = false;

@@ -42,7 +42,8 @@ struct ConvTcParams {
     int num_tiles;         // B * tiles_h * tiles_w
     uint32_t magic_tpc, magic_tw;   // ceil(2^40 / d) >> 8 style magics, see fast_div
     int ks, stride, pad;
-    int cout;
+    int cout;              // output channels of THIS launch (<= NPAD)
+    int n_off, ldc;        // first output channel / channel pitch of the output map (cout > 128 runs as 128-wide slices)
     int relu_first;
     const float* bias;     // may be null
     const float* scale;
@@ -166,9 +167,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 3) tmem_alloc<S::kTmemCols>(tmem_ptr);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + 128) {
         const int n = threadIdx.x - 128;
-        par[n] = (p.bias && n < p.cout) ? p.bias[n] : 0.f;
-        par[128 + n] = n < p.cout ? p.scale[n] : 0.f;
-        par[256 + n] = n < p.cout ? p.shift[n] : 0.f;
+        par[n] = (p.bias && n < p.cout) ? p.bias[p.n_off + n] : 0.f;
+        par[128 + n] = n < p.cout ? p.scale[p.n_off + n] : 0.f;
+        par[256 + n] = n < p.cout ? p.shift[p.n_off + n] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -181,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (S::kResidentB) {
                 mbar_expect_tx(b_full, (uint32_t)S::kNumKb * NPAD * S::kSwz);
                 for (int kb = 0; kb < S::kNumKb; ++kb)
-                    tma_load_2d(smem + kb * S::kBBytes, &tmB, b_full, (kb / S::kChunks) * CIN + (kb % S::kChunks) * S::CK, 0);
+                    tma_load_2d(smem + kb * S::kBBytes, &tmB, b_full, (kb / S::kChunks) * CIN + (kb % S::kChunks) * S::CK, p.n_off);
             }
             const uint32_t a_bytes = (uint32_t)p.BW * p.BH * S::kSwz;
             const uint32_t stage_tx = S::kKbPerStage * (a_bytes + (S::kResidentB ? 0u : (uint32_t)NPAD * S::kSwz));
@@ -217,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     hi0 + tap / KS, b);
                         if (!S::kResidentB)
                             tma_load_2d(dst + S::kKbPerStage * S::kABytes + j * S::kBBytes, &tmB, &full[st],
-                                        tap * CIN + chunk * S::CK, 0);
+                                        tap * CIN + chunk * S::CK, p.n_off);
                     }
                 }
             }
@@ -387,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (OUT == OUT_DIRECT) {
                     if (valid) {
                         const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
-                        __half* o = p.out + pix * p.cout + nb;     // cout is a multiple of 32 on this path
+                        __half* o = p.out + pix * p.ldc + p.n_off + nb;     // cout is a multiple of 32 on this path
                         // 256-bit stores: every thread writes whole 32-byte sectors
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
@@ -452,7 +453,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int n = q * 32 + lane;
                     if (n < p.cout) {
                         const float* red = reinterpret_cast<const float*>(smem + S::kRedOffset) + grp * 1024 + par_buf * 512;
-                        p.se_part[(size_t)tile * p.cout + n] = (red[n] + red[128 + n]) + (red[256 + n] + red[384 + n]);
+                        p.se_part[(size_t)tile * p.ldc + p.n_off + n] = (red[n] + red[128 + n]) + (red[256 + n] + red[384 + n]);
                     }
                 }
             }
@@ -493,7 +494,7 @@ int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straigh
 int g_halo = 3;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
-int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, cudaStream_t s) {
+int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s) {
     using S = ConvCfg<CIN, NPAD, TAPS, HALO, OUT>;
     ConvTcParams p;
     p.ks = c.ks; p.stride = c.stride; p.pad = c.ks / 2;
@@ -509,7 +510,7 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     if ((uint64_t)p.num_tiles * (uint64_t)p.tiles_per_clip >= (1ull << 32)) return -1;   // fast_div exactness
     p.magic_tpc = make_magic((uint32_t)p.tiles_per_clip);
     p.magic_tw = make_magic((uint32_t)p.tiles_w);
-    p.cout = c.cout; p.relu_first = c.relu_first;
+    p.cout = c.cout - n_off < 128 ? c.cout - n_off : 128; p.n_off = n_off; p.ldc = c.cout; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
     p.out = out; p.se_part = se_part; p.debug = g_debug;
 
@@ -528,7 +529,7 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     const uint32_t bB[2] = {(uint32_t)S::CK, (uint32_t)NPAD};
     if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, swz)) return -1;
     if (OUT == OUT_TMA) {
-        if (c.cout != NPAD) return -1;
+        if (c.cout != NPAD || n_off) return -1;
         const uint64_t dO[4] = {(uint64_t)NPAD, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)B};
         const uint64_t sO[3] = {(uint64_t)NPAD * 2, (uint64_t)p.Wo * NPAD * 2, (uint64_t)p.Ho * p.Wo * NPAD * 2};
         const uint32_t bO[4] = {(uint32_t)NPAD, (uint32_t)p.BW, (uint32_t)p.BH, 1};
@@ -557,6 +558,7 @@ int set_attr() {
     X(64, 64, 9, false, OUT_TMA) X(32, 64, 9, false, OUT_TMA) X(32, 64, 1, false, OUT_TMA)            \
     X(64, 128, 9, false, OUT_DIRECT) X(64, 128, 1, false, OUT_DIRECT) X(128, 128, 9, false, OUT_DIRECT) \
     X(32, 32, 9, true, OUT_DIRECT) X(64, 64, 9, true, OUT_DIRECT)                                     \
+    X(256, 128, 9, false, OUT_DIRECT) X(128, 128, 1, false, OUT_DIRECT)                               \
     X(128, 48, 9, false, OUT_NCHW) X(128, 64, 9, false, OUT_NCHW)
 
 int conv_tc_init_device() {
@@ -591,12 +593,19 @@ int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo) {
 int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw, float* se_part,
                    cudaStream_t s) {
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
-    if (c.cout > 128 || (!nchw && c.cout % 32)) return -1;
+    if ((c.cout > 128 && (nchw || c.cout % 128)) || (!nchw && c.cout % 32)) return -1;
     const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
     const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & 2))))) ? OUT_TMA : OUT_DIRECT);
 #define X(CI, NP, TP, HL, OU)                                                                   \
     if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU)         \
-        return launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, s);
+    {                                                                                           \
+        int n = 0;                                                                              \
+        for (int n_off = 0; n_off < c.cout; n_off += 128) {                                     \
+            if (launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, n_off, s) < 0) return -1; \
+            ++n;                                                                                \
+        }                                                                                       \
+        return n;                                                                               \
+    }
     EGX_CONV_INSTANCES(X)
 #undef X
     return -1;

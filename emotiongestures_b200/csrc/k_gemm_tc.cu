@@ -22,7 +22,6 @@ using namespace tc;
 constexpr int GM = 128;          // tile rows (UMMA M)
 constexpr int GK = 64;           // fp16 elements per K block = one 128-byte swizzle row
 constexpr int kGemmThreads = 320;
-constexpr int kMaxBias = 2048;   // widest N staged in shared memory
 
 template <int BN>
 struct GemmCfg {
@@ -31,8 +30,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = BN == 256 ? 4 : 6;
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kBiasOffset = kBarOffset + 256;
-    static constexpr int kTotal = kBiasOffset + kMaxBias * 4 + 1024;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -57,7 +55,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = empty + S::kStages;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* sbias = reinterpret_cast<float*>(smem + S::kBiasOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + GK - 1) / GK;
@@ -72,7 +69,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_ptr);
-    for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads) sbias[i] = (ep.bias && i < N) ? ep.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -96,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GM, BN);
+            constexpr uint32_t kDescHi = smem_desc_hi<128>();
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1;
@@ -106,12 +103,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int st = it % S::kStages;
                     mbar_wait(&full[st], (it / S::kStages) & 1);
                     tc_fence_after();
-                    const uint32_t a = smem_u32(smem + st * S::kStageBytes);
-                    const uint32_t b = a + S::kABytes;
+                    const uint32_t a_lo = smem_desc_lo(smem_u32(smem + st * S::kStageBytes));
+                    if (kb == 0) {
 #pragma unroll
-                    for (int k = 0; k < GK / 16; ++k)
-                        umma_f16(d, make_smem_desc<128>(a + k * 32), make_smem_desc<128>(b + k * 32), idesc,
-                                 (kb | k) != 0);
+                        for (int k = 0; k < GK / 16; ++k)
+                            umma_f16_lo<kDescHi>(d, a_lo + 2 * k, a_lo + (S::kABytes >> 4) + 2 * k, idesc, k != 0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < GK / 16; ++k)
+                            umma_f16_lo<kDescHi>(d, a_lo + 2 * k, a_lo + (S::kABytes >> 4) + 2 * k, idesc, true);
+                    }
                     umma_commit(&empty[st]);
                 }
                 umma_commit(&tmem_full[acc]);
@@ -144,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (full_chunk) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 bi = *reinterpret_cast<const float4*>(sbias + nb + 4 * j4);
+                            const float4 bi = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (add_row) {
                                 if (add_vec) ad = __ldg(reinterpret_cast<const float4*>(add_row + nb) + j4);
@@ -165,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int n = nb + j;
                             float t = v[j];
                             if (n < N) {
-                                t += sbias[n];
+                                if (ep.bias) t += __ldg(ep.bias + n);
                                 if (relu) t = fmaxf(t, 0.f);
                                 if (add_row) t += __ldg(add_row + n);
                             }
@@ -267,7 +268,6 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 // A: [M][K] fp16 with row pitch lda (elements, multiple of 8); W: [N][K] fp16 with row pitch ldw.
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
-    if (N > kMaxBias) return -1;
     GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16};
     if (N % 256 == 0) return launch_bn<256>(A, lda, W, ldw, M, N, K, ep, s);
     return launch_bn<128>(A, lda, W, ldw, M, N, K, ep, s);

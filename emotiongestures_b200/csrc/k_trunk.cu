@@ -252,7 +252,7 @@ se_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, const float*
                 int n_part, int HW, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
                 const float* __restrict__ w2, const float* __restrict__ b2, int pix_per_block,
                 T* __restrict__ out) {
-    __shared__ float mean[128], hid[16], gate[128];
+    __shared__ float mean[256], hid[32], gate[256];
     const int b = blockIdx.y;
     if (threadIdx.x < C) {
         float t = 0.f;

@@ -73,13 +73,13 @@ class _Trunk(nn.Module):
     LAYERS = (3, 4, 6)
     FILTERS = (32, 64, 128)
 
-    def __init__(self):
+    def __init__(self, layers=None, filters=None):
         super().__init__()
-        f = self.FILTERS
+        f = filters or self.FILTERS
         self.conv1 = nn.Conv2d(1, f[0], 3, stride=1, padding=1)
         self.bn1 = nn.BatchNorm2d(f[0])
         cin = f[0]
-        for li, (n, c) in enumerate(zip(self.LAYERS, f), start=1):
+        for li, (n, c) in enumerate(zip(layers or self.LAYERS, f), start=1):
             blocks = []
             for b in range(n):
                 blocks.append(_SEBlock(cin, c, 2 if (b == 0 and li > 1) else 1))

@@ -147,6 +147,13 @@ EGX_API size_t egx_row_features_workspace(const egx_handle* h, int64_t n_rows);
 EGX_API int  egx_row_features(egx_handle* h, const float* rows, int64_t n_rows, int dim, float* out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces: EmotionNet.forward (model/audio_emotion_classifer.py:38-49; trunk model/emotion_ResNetSE34V2.py:57-72),
+ * weights under the "emotion_net." prefix.  spec (n,128,W) f32 log-mel, W even with 256*(128/8)*(W/8 rounded up) = 65536
+ * for the checkpointed net (W = 124) -> logits (n,8) f32 (the reference also leaves the softmax off). */
+EGX_API size_t egx_emotion_net_workspace(const egx_handle* h, int n_clips, int n_mels, int n_cols);
+EGX_API int  egx_emotion_net_forward(egx_handle* h, const float* spec, int n_clips, int n_mels, int n_cols,
+                             float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Parity probe of the tcgen05 Linear kernel alone: out = [relu](A W^T + bias) + addend, A (M,K), W (N,K),
  * out (M,N) f32; operands are rounded to fp16 inside.  Synchronises the stream (test-only). */
 EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias,

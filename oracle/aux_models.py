@@ -75,5 +75,16 @@ def fgd_latent(sd, rows):
     return _chain(sd, "Encoder", (0, 2, 4), rows)
 
 
+def emotion_net(sd, mfcc, taps=None):
+    """model/audio_emotion_classifer.py:38-49 over the trunk of model/emotion_ResNetSE34V2.py:57-72 (the same
+    SEBasicBlock as the generator's, one more stage)."""
+    from oracle import generator as og
+    feat = og.trunk(sd, "emotion_encoder", mfcc.unsqueeze(1), layers=(3, 4, 6, 3), taps=taps)
+    x = feat.reshape(feat.shape[0], -1)
+    for i in (0, 2, 4, 6, 8):
+        x = F.relu(_lin(sd, f"emotion_eocder_fc.{i}", x))
+    return _lin(sd, "last_fc", x)
+
+
 def cast(sd, dtype):
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -152,8 +152,40 @@ def main():
 
 
 if __name__ == "__main__":
-    torch.set_num_threads(4)
-    main()
+    torch.set_num_threads(8)
+    if "--emotion-net" not in sys.argv:
+        main()
     for f in sorted(os.listdir(GOLD)):
         if f.startswith("aux_"):
             print(f"  {f}: {os.path.getsize(os.path.join(GOLD, f)) / 1024:.0f} KiB")
+
+
+def emotion_net_golden():
+    """C3: model/audio_emotion_classifer.py EmotionNet (1 GB of fp32 weights: kept out of main())."""
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("fasttext", types.ModuleType("fasttext"))
+    import importlib
+    ref = importlib.import_module("model.audio_emotion_classifer").EmotionNet().eval()
+    mine = mirrors.EmotionNet()
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 16)
+    del mine
+    ref.load_state_dict(sd)
+    n = 2
+    spec = torch.from_numpy(synth.synth_spec(n, 128, 124, 16))
+    taps_ref = {}
+    hook = ref.emotion_encoder.register_forward_hook(lambda _m, _i, o: taps_ref.__setitem__("layer4", o.detach().clone()))
+    with torch.no_grad():
+        r = ref(spec)
+    hook.remove()
+    taps = {}
+    with torch.no_grad():
+        o = oa.emotion_net(sd, spec, taps)
+    print(f"  emotion_net logits: oracle vs reference {rel(o, r):.2e}; layer4 {rel(taps['layer4'], taps_ref['layer4']):.2e}")
+    assert rel(o, r) <= 2e-6 and rel(taps["layer4"], taps_ref["layer4"]) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_emotion_net.npz"), seed=16, n=n, logits=r.numpy(),
+                        layer4_mean=taps_ref["layer4"].double().mean(dim=(2, 3)).numpy().astype(np.float32))
+
+
+if __name__ == "__main__" and "--emotion-net" in sys.argv:
+    emotion_net_golden()

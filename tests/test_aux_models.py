@@ -37,12 +37,20 @@ CASES = {
     "motion_ae": (mirrors.MotionAE, 13, (126, 128)),
     "pose_enc": (mirrors.PoseEncoderConv, 14, (60, 282)),
     "fgd_mlp": (mirrors.FGDNet, 15, ()),
+    "emotion_net": (mirrors.EmotionNet, 16, ()),     # 1 GB of fp32 weights: built once per session
 }
+_big = {}
 
 
 def reference_and_inputs(name):
     g = load_golden("aux_" + name)
     cls, seed, args = CASES[name]
+    if name == "emotion_net":
+        if name not in _big:
+            _big[name] = build(cls, seed, *args)
+        m, sd = _big[name]
+        ins = dict(mfcc=torch.from_numpy(synth.synth_spec(int(g["n"]), 128, 124, seed)))
+        return m, sd, ins, {"logits": torch.from_numpy(g["logits"])}
     m, sd = build(cls, seed, *args)
     if name == "cvae":
         n = int(g["n"])
@@ -75,6 +83,8 @@ def oracle_outputs(name, sd, ins):
             return {"z": oa.pose_encoder(sd, ins["poses"], "encoder.")}
         if name == "pose_enc":
             return {"mu": oa.pose_encoder(sd, ins["poses"], "", fc_mu=True)}
+        if name == "emotion_net":
+            return {"logits": oa.emotion_net(sd, ins["mfcc"])}
         return {"latent": oa.fgd_latent(sd, ins["poses"])}
 
 
@@ -119,6 +129,8 @@ def device_outputs(name, m, ins):
             return {"z": m(d["poses"])[1]}
         if name == "pose_enc":
             return {"mu": m(d["poses"], False)[1]}
+        if name == "emotion_net":
+            return {"logits": m(d["mfcc"])}
         return {"latent": m(d["poses"])[1]}
 
 
@@ -127,7 +139,7 @@ def device_outputs(name, m, ins):
 def test_cuda_matches_reference_golden(name):
     m, _, ins, ref = reference_and_inputs(name)
     got = device_outputs(name, m, ins)
-    tol = 2e-3 if name == "fgd_mlp" else 2e-5
+    tol = {"fgd_mlp": 2e-3, "emotion_net": 2e-3}.get(name, 2e-5)
     for k, r in ref.items():
         g = got[k].cpu()
         assert g.shape == r.shape and not torch.isnan(g).any()
