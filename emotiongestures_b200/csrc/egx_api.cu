@@ -645,15 +645,11 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, nullptr, s));
     }
     StageScope sc5(h, 5);
-    if (linear_tc(h, w.a_fc1, sl.fcin, HW3, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.a_fc2, sl.t16, d, R, sl.spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.a_fc, sl.fcin, HW3, R, sl.spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
     LAUNCH(h, launch_prior_conv<__half>(w, prior, B, c.prior_frames, F, P, sl.pconv16, P8, s));
-    if (linear_tc(h, w.p_fc1, sl.pconv16, P8, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.p_fc2, sl.t16, d, R, sl.prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.emo0, sl.spec16, d, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.emo2, sl.t16, d, R, emo_feat, d, sl.emo16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.sem0, sl.spec16, d, R, nullptr, 0, sl.t16, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.sem2, sl.t16, d, R, sem_feat, d, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.p_fc, sl.pconv16, P8, R, sl.prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.emo, sl.spec16, d, R, emo_feat, d, sl.emo16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.sem, sl.spec16, d, R, sem_feat, d, nullptr, 0, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.hdr[0], sl.emo16, F * d, B, nullptr, 0, sl.h0, d, 1, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.hdr[1], sl.h0, d, B, nullptr, 0, sl.h1, 256, 1, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.hdr[2], sl.h1, 256, B, nullptr, 0, sl.h2, 64, 1, nullptr, 0, s)) return 1;
@@ -696,10 +692,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         dx32 = o32; dx16 = o16;
     }
     StageScope sc5b(h, 5);
-    if (linear_tc(h, w.post[0], sl.dec16, d, R, nullptr, 0, sl.post0, 4 * d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.post[1], sl.post0, 4 * d, R, nullptr, 0, sl.post1, d, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.post[2], sl.post1, d, R, nullptr, 0, sl.post2, P8, 0, nullptr, 0, s)) return 1;
-    if (linear_tc(h, w.post[3], sl.post2, P8, R, poses, P, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.post_all, sl.dec16, d, R, poses, P, nullptr, 0, 0, nullptr, 0, s)) return 1;
     return 0;
 }
 
@@ -1010,6 +1003,26 @@ EmoSlots plan_emotion(int B, int H0, int W0, Plan& p) {
     return s;
 }
 
+// Linear chain `keys` (state_dict prefixes, dims[i] -> dims[i+1]) as ONE LinearW
+bool make_collapsed(egx_handle* h, std::initializer_list<std::string> keys, std::initializer_list<int> dims, LinearW* out) {
+    auto d = dims.begin();
+    Affine acc;
+    bool first = true;
+    for (const auto& k : keys) {
+        Affine a;
+        if (!get_affine(h, k, d[0], d[1], &a)) return false;
+        acc = first ? a : compose(acc, a);
+        first = false;
+        ++d;
+    }
+    out->in = acc.in; out->out = acc.out;
+    const std::vector<float> wf = to_f32(acc.W);
+    out->w = upload(h, wf);
+    out->b = upload(h, to_f32(acc.b));
+    add_f16_copy(h, wf, acc.out, acc.in, out);
+    return out->w && out->b && out->w16;
+}
+
 // D1: per-frame MLP of model/FGD.py:30-41 (Encoder: Linear(282,512) Linear(512,512) Linear(512,512), Dropouts between)
 int pack_fgd_mlp(egx_handle* h) {
     BucketScope scope(h, "fgd_mlp");
@@ -1150,6 +1163,13 @@ int egx_finalize_weights(egx_handle* h) {
     const int post_in[4] = {d, 4 * d, d, P}, post_out[4] = {4 * d, d, P, P};
     for (int i = 0; i < 4; ++i)
         if (!make_linear(h, "post_projector." + std::to_string(2 * i), post_in[i], post_out[i], true, &w.post[i])) return 1;
+    if (!make_collapsed(h, {"audio_encoder.fc1", "audio_encoder.fc2"}, {h->H[2] * h->W[2], d, d}, &w.a_fc) ||
+        !make_collapsed(h, {"prior_seq_encoder.fc1", "prior_seq_encoder.fc2"}, {P, d, d}, &w.p_fc) ||
+        !make_collapsed(h, {"emotion_proj.0", "emotion_proj.2"}, {d, d, d}, &w.emo) ||
+        !make_collapsed(h, {"semantic_proj.0", "semantic_proj.2"}, {d, d, d}, &w.sem) ||
+        !make_collapsed(h, {"post_projector.0", "post_projector.2", "post_projector.4", "post_projector.6"}, {d, 4 * d, d, P, P},
+                        &w.post_all))
+        return 1;
     {
         const HostTensor* pt;
         if (!need(h, "encoder.position_enc.pos_table", {1, c.n_position, d}, &pt)) return 1;

@@ -74,6 +74,9 @@ struct Weights {
     LinearW emo0, emo2, sem0, sem2, fus0, fus2;
     LinearW hdr[4];
     LinearW post[4];
+    // tensor-core arm: Linear -> Dropout -> Linear chains (no activation between them; Dropout is the identity in
+    // eval) collapsed into one affine map, composed in float64 at weight-packing time
+    LinearW a_fc, p_fc, emo, sem, post_all;
     float* pos_table = nullptr;       // [n_position][d]
     std::vector<MHAW> enc_attn, dec_attn;
     std::vector<FFNW> enc_ffn, dec_ffn;
