@@ -464,6 +464,231 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 3) tmem_dealloc<S::kTmemCols>(tmem_base);
 }
 
+// =================================================================================================================
+// 128 -> 128 channel 3x3 stride-1 convolutions (layer 3: 11 of the 29 trunk convolutions).
+// The generic kernel streams a 16 KB activation box AND a 16 KB weight block for every 4 MMAs: 128 B/clk per SM, far
+// above what L2 can deliver to 148 SMs, and its six 256-cycle ring stages cannot cover the TMA round trip.  Here
+//   * activations use halo reuse: per tile one (BH+2) x (BW+2) patch per 64-channel half (2 x 22 KB), all nine taps
+//     are row-shifted UMMA descriptors over it;
+//   * the 288 KB of weights stream through a 7-deep ring of 16 KB (tap, half) blocks, and every block feeds TWO tiles
+//     (two accumulators), so weight traffic per tile halves and a ring stage carries 8 MMAs = 512 tensor cycles;
+//   * the K loop runs half-major (all taps of channels 0-63, then of 64-127): a tile's first-half patch is free for
+//     the next super-tile's load while the second half is still being multiplied — double buffering without the smem.
+// warp 0: TMA producer; warps 1,2: one MMA issuer per tile of the pair; warp 3: TMEM alloc; warps 4-11: two epilogue
+// groups (one per tile of the pair), accumulators double-buffered across super-tiles (2 x 2 x 128 TMEM columns).
+// =================================================================================================================
+struct C128 {
+    static constexpr int kPatchBytes = kPatchRows * 128;          // one 64-channel half of one tile's patch
+    static constexpr int kBBytes = 128 * 128;                     // 128 couts x 64 channels of one tap
+    static constexpr int kBStages = 7;
+    static constexpr int kAOffset = 0;                            // [tile 2][half 2]
+    static constexpr int kBOffset = 4 * kPatchBytes;
+    static constexpr int kBarOffset = kBOffset + kBStages * kBBytes;
+    static constexpr int kParOffset = kBarOffset + 256;
+    static constexpr int kRedOffset = kParOffset + 3 * 128 * 4;
+    static constexpr int kTotal = kRedOffset + 2 * 2 * 4 * 128 * 4 + 1024;
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
+    using S = C128;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);    // [tile * 2 + half]
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + S::kBStages;
+    uint64_t* tmem_full = b_empty + S::kBStages;     // [buf * 2 + tile]
+    uint64_t* tmem_empty = tmem_full + 4;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+    float* par = reinterpret_cast<float*>(smem + S::kParOffset);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_super = (p.num_tiles + 1) >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < S::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc<512>(tmem_ptr);
+    if (threadIdx.x >= 128 && threadIdx.x < 256) {
+        const int n = threadIdx.x - 128;
+        par[n] = p.bias ? p.bias[n] : 0.f;
+        par[128 + n] = p.scale[n];
+        par[256 + n] = p.shift[n];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            const uint32_t a_tx = (uint32_t)p.MW * (p.BH + 2) * 128;
+            uint32_t it = 0, n = 0;
+            for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+                int wi0[2], hi0[2], bb[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t tile = 2 * u + t;
+                    const uint32_t b = fast_div(tile, p.magic_tpc), tt = tile - b * p.tiles_per_clip;
+                    const uint32_t th = fast_div(tt, p.magic_tw), tw = tt - th * p.tiles_w;
+                    wi0[t] = (int)tw * p.BW - 1; hi0[t] = (int)th * p.BH - 1; bb[t] = (int)b;   // clip >= B: zero fill
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(&a_empty[t * 2 + ch], (n & 1) ^ 1);
+                        mbar_expect_tx(&a_full[t * 2 + ch], a_tx);
+                        tma_load_4d(smem + S::kAOffset + (t * 2 + ch) * S::kPatchBytes, &tmA, &a_full[t * 2 + ch], ch * 64,
+                                    wi0[t], hi0[t], bb[t]);
+                    }
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        const int st = it % S::kBStages;
+                        mbar_wait(&b_empty[st], ((it / S::kBStages) & 1) ^ 1);
+                        mbar_expect_tx(&b_full[st], S::kBBytes);
+                        tma_load_2d(smem + S::kBOffset + st * S::kBBytes, &tmB, &b_full[st], tap * 128 + ch * 64, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ================= MMA issuers: warp 1 -> first tile of the pair, warp 2 -> second =================
+        const uint32_t t = warp - 1;
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(128, 128);
+            constexpr uint32_t kDescHi = smem_desc_hi<128>();
+            const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem + S::kBOffset));
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + S::kAOffset + t * 2 * S::kPatchBytes));
+            const uint32_t row_off[3] = {0u, (uint32_t)(p.MW * 128) >> 4, (uint32_t)(2 * p.MW * 128) >> 4};
+            uint32_t it = 0, n = 0;
+            for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+                const uint32_t buf = n & 1;
+                mbar_wait(&tmem_empty[buf * 2 + t], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (buf * 2 + t) * 128;
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    mbar_wait(&a_full[t * 2 + ch], n & 1);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + ((ch * S::kPatchBytes) >> 4);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
+                        const int st = it % S::kBStages;
+                        mbar_wait(&b_full[st], (it / S::kBStages) & 1);
+                        tc_fence_after();
+                        const uint32_t a_tap = a_lo + row_off[tap / 3] + (tap % 3) * (128 >> 4);
+                        const uint32_t b_lo = b_lo0 + ((st * S::kBBytes) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (tap == 0 && k == 0 && ch == 0) umma_f16_lo<kDescHi>(d, a_tap, b_lo, idesc, false);
+                            else umma_f16_lo<kDescHi>(d, a_tap + 2 * k, b_lo + 2 * k, idesc, true);
+                        }
+                        umma_commit(&b_empty[st]);
+                    }
+                    umma_commit(&a_empty[t * 2 + ch]);
+                }
+                umma_commit(&tmem_full[buf * 2 + t]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: group g drains the accumulator of tile g of every pair =================
+        const int grp = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int ph_ = r / p.MW, pw_ = r % p.MW;
+        const bool in_patch = ph_ < p.BH && pw_ < p.BW;
+        const bool relu_first = p.relu_first != 0;
+        const bool has_bias = p.bias != nullptr;
+        const bool se = p.se_part != nullptr;
+        const uint32_t par_u32 = smem_u32(par);
+        const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
+        uint32_t n = 0;
+        for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+            const uint32_t tile = 2 * u + grp;
+            const uint32_t b = fast_div(tile, p.magic_tpc), tt = tile - b * p.tiles_per_clip;
+            const uint32_t th = fast_div(tt, p.magic_tw), tw = tt - th * p.tiles_w;
+            const int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
+            const bool live = tile < (uint32_t)p.num_tiles;
+            const bool valid = live && in_patch && ho < p.Ho && wo < p.Wo;
+            const uint32_t buf = n & 1, par_buf = n & 1;
+            mbar_wait(&tmem_full[buf * 2 + grp], (n >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (buf * 2 + grp) * 128 + ((uint32_t)(q * 32) << 16);
+            __half* o = p.out + (((size_t)b * p.Ho + ho) * p.Wo + wo) * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                const int nb = c * 32;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 sc = lds128(par_u32 + (128 + nb + 4 * j4) * 4);
+                    const float4 sh = lds128(par_u32 + (256 + nb + 4 * j4) * 4);
+                    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_bias) bi = lds128(par_u32 + (nb + 4 * j4) * 4);
+                    const float sv[4] = {sc.x, sc.y, sc.z, sc.w}, hv[4] = {sh.x, sh.y, sh.z, sh.w}, bv[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float tv = v[4 * j4 + e] + bv[e];
+                        if (relu_first) tv = fmaxf(tv, 0.f);
+                        v[4 * j4 + e] = fmaf(tv, sv[e], hv[e]);
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + nb + 16 * j),
+                                     "r"(pack_h2(v[16 * j], v[16 * j + 1])), "r"(pack_h2(v[16 * j + 2], v[16 * j + 3])),
+                                     "r"(pack_h2(v[16 * j + 4], v[16 * j + 5])), "r"(pack_h2(v[16 * j + 6], v[16 * j + 7])),
+                                     "r"(pack_h2(v[16 * j + 8], v[16 * j + 9])), "r"(pack_h2(v[16 * j + 10], v[16 * j + 11])),
+                                     "r"(pack_h2(v[16 * j + 12], v[16 * j + 13])), "r"(pack_h2(v[16 * j + 14], v[16 * j + 15]))
+                                     : "memory");
+                }
+                if (se) {
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const bool upper = (lane & step) != 0;
+#pragma unroll
+                        for (int j = 0; j < step; ++j) {
+                            const float send = upper ? v[j] : v[j + step];
+                            const float keep = upper ? v[j + step] : v[j];
+                            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                        }
+                    }
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(red_u32 + (par_buf * 512 + q * 128 + nb + lane) * 4), "f"(v[0]) : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf * 2 + grp]);
+            if (se) {
+                named_bar_sync(1 + grp, 128);
+                if (live) {
+                    const float* red = reinterpret_cast<const float*>(smem + S::kRedOffset) + grp * 1024 + par_buf * 512;
+                    p.se_part[(size_t)tile * 128 + r] = (red[r] + red[128 + r]) + (red[256 + r] + red[384 + r]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc<512>(tmem_base);
+}
+
 // (BW, BH) with BW*BH <= 128 that wastes the fewest MMA rows on an Ho x Wo map
 void pick_patch(int Ho, int Wo, int* bw, int* bh) {
     long best = -1;
@@ -491,7 +716,7 @@ void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
 int g_num_sms = 0;
 int g_debug = 0;
 int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too
-int g_halo = 3;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
+int g_halo = 7;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
 int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s) {
@@ -544,6 +769,37 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, cudaStream_t s) {
+    ConvTcParams p;
+    p.ks = 3; p.stride = 1; p.pad = 1;
+    p.Ho = Hin; p.Wo = Win;
+    pick_halo_patch(p.Ho, p.Wo, &p.BW, &p.BH);
+    p.MW = p.BW + 2;
+    p.tiles_w = (p.Wo + p.BW - 1) / p.BW;
+    p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
+    p.tiles_per_clip = p.tiles_w * p.tiles_h;
+    p.num_tiles = B * p.tiles_per_clip;
+    if ((uint64_t)(p.num_tiles + 1) * (uint64_t)p.tiles_per_clip >= (1ull << 32)) return -1;
+    p.magic_tpc = make_magic((uint32_t)p.tiles_per_clip);
+    p.magic_tw = make_magic((uint32_t)p.tiles_w);
+    p.cout = 128; p.n_off = 0; p.ldc = 128; p.relu_first = c.relu_first;
+    p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
+    p.out = out; p.se_part = se_part; p.debug = g_debug;
+    CUtensorMap ta, tb;
+    const uint64_t dA[4] = {128, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    const uint64_t sA[3] = {256, (uint64_t)Win * 256, (uint64_t)Hin * Win * 256};
+    const uint32_t bA[4] = {64, (uint32_t)p.MW, (uint32_t)(p.BH + 2), 1};
+    if (!make_tmap_f16(&ta, in, 4, dA, sA, bA, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    const uint64_t dB[2] = {9 * 128, 128};
+    const uint64_t sB[1] = {9 * 128 * 2};
+    const uint32_t bB[2] = {64, 128};
+    if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    const int n_super = (p.num_tiles + 1) / 2;
+    const int grid = n_super < g_num_sms ? n_super : g_num_sms;
+    conv128_tc_kernel<<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
 int set_attr() {
     return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -568,7 +824,7 @@ int conv_tc_init_device() {
     if (const char* e = getenv("EGX_CONV_HALO")) g_halo = atoi(e);
     if (const char* e = getenv("EGX_CONV_DEBUG")) g_debug = atoi(e);
     if (const char* e = getenv("EGX_CONV_OUT")) g_out_direct = atoi(e);
-    int rc = 0;
+    int rc = cudaFuncSetAttribute(conv128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
 #define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU>();
     EGX_CONV_INSTANCES(X)
 #undef X
@@ -577,7 +833,7 @@ int conv_tc_init_device() {
 
 static bool use_halo(int cin, int cout, int ks, int stride, int nchw) {
     if (ks != 3 || stride != 1 || nchw || cin != cout) return false;
-    return (cin == 64 && g_halo >= 1) || (cin == 32 && (g_halo & 2));
+    return (cin == 64 && g_halo >= 1) || (cin == 32 && (g_halo & 2)) || (cin == 128 && (g_halo & 4));
 }
 
 // SE partial-sum slots a conv writes per clip (tiles per clip) for an Ho x Wo output map
@@ -595,6 +851,7 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
     if ((c.cout > 128 && (nchw || c.cout % 128)) || (!nchw && c.cout % 32)) return -1;
     const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
+    if (halo && c.cin == 128) return launch_conv128(c, in, B, Hin, Win, out, se_part, s);
     const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & 2))))) ? OUT_TMA : OUT_DIRECT);
 #define X(CI, NP, TP, HL, OU)                                                                   \
     if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU)         \
