@@ -211,8 +211,8 @@ bool build_logmel_tables(egx_handle* h) {
     const int n_fft = 1024, n_bins = 513, n_mels = 128;
     std::vector<float> window(n_fft);
     for (int i = 0; i < n_fft; ++i) window[i] = (float)(0.5 - 0.5 * std::cos(2.0 * kPi * i / n_fft));
-    std::vector<float2> tw512(256), tw1024(513);
-    for (int k = 0; k < 256; ++k)
+    std::vector<float2> tw512(512), tw1024(513);
+    for (int k = 0; k < 512; ++k)
         tw512[k] = make_float2((float)std::cos(-2.0 * kPi * k / 512), (float)std::sin(-2.0 * kPi * k / 512));
     for (int k = 0; k <= 512; ++k)
         tw1024[k] = make_float2((float)std::cos(-2.0 * kPi * k / 1024), (float)std::sin(-2.0 * kPi * k / 1024));

@@ -170,7 +170,9 @@ attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int 
 }
 
 // Prior-pose encoder front: Conv1d(p->F,k3) -> ReLU -> BN -> Conv1d(F->F,k3) -> ReLU -> BN along
-// the pose axis (channels = frames).  One CTA per clip.
+// the pose axis (channels = frames).  One CTA per clip.  The second convolution carries the work (F*F*3 MACs per
+// output column): its weights sit in shared memory as [c][k][f] so that a thread producing 4 frames x 1 column
+// issues 3 broadcast 16-byte weight loads + 3 activation loads per 12 FMAs.
 template <class T>
 __global__ void __launch_bounds__(256)
 prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
@@ -179,11 +181,16 @@ prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
                   const float* __restrict__ w2, const float* __restrict__ b2,
                   const float* __restrict__ s2, const float* __restrict__ t2,
                   T* __restrict__ out, int ldo) {
-    extern __shared__ float sm[];
-    const int PW = P + 2;
-    float* sin_ = sm;                 // [p][P+2] zero-padded
+    extern __shared__ __align__(16) float sm[];
+    const int PW = P + 2, F4 = (F + 3) & ~3;
+    float* w2s = sm;                  // [F][3][F4]  (input frame c, tap k, output frame f)
+    float* sin_ = w2s + F * 3 * F4;   // [p][P+2] zero-padded
     float* mid = sin_ + p * PW;       // [F][P+2] zero-padded
     const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < F * 3 * F4; i += blockDim.x) {
+        const int f = i % F4, k = (i / F4) % 3, c = i / (3 * F4);
+        w2s[i] = f < F ? w2[(f * F + c) * 3 + k] : 0.f;
+    }
     for (int i = threadIdx.x; i < p * PW; i += blockDim.x) {
         const int c = i / PW, x = i % PW - 1;
         sin_[i] = (x >= 0 && x < P) ? prior[((size_t)b * p + c) * P + x] : 0.f;
@@ -199,13 +206,25 @@ prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
         mid[f * PW + x + 1] = fmaxf(a, 0.f) * s1[f] + t1[f];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < F * P; i += blockDim.x) {
-        const int f = i / P, x = i % P;
-        float a = b2[f];
-        for (int c = 0; c < F; ++c)
+    for (int i = threadIdx.x; i < (F4 / 4) * P; i += blockDim.x) {
+        const int fg = i / P, x = i % P;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < F; ++c) {
+            const float* m = mid + c * PW + x;
+            const float m0 = m[0], m1 = m[1], m2 = m[2];
+            const float4 wa = *reinterpret_cast<const float4*>(w2s + (c * 3 + 0) * F4 + fg * 4);
+            const float4 wb = *reinterpret_cast<const float4*>(w2s + (c * 3 + 1) * F4 + fg * 4);
+            const float4 wc = *reinterpret_cast<const float4*>(w2s + (c * 3 + 2) * F4 + fg * 4);
+            a[0] = fmaf(wa.x, m0, fmaf(wb.x, m1, fmaf(wc.x, m2, a[0])));
+            a[1] = fmaf(wa.y, m0, fmaf(wb.y, m1, fmaf(wc.y, m2, a[1])));
+            a[2] = fmaf(wa.z, m0, fmaf(wb.z, m1, fmaf(wc.z, m2, a[2])));
+            a[3] = fmaf(wa.w, m0, fmaf(wb.w, m1, fmaf(wc.w, m2, a[3])));
+        }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) a = fmaf(w2[(f * F + c) * 3 + k], mid[c * PW + x + k], a);
-        out[((size_t)b * F + f) * ldo + x] = T(fmaxf(a, 0.f) * s2[f] + t2[f]);
+        for (int j = 0; j < 4; ++j) {
+            const int f = fg * 4 + j;
+            if (f < F) out[((size_t)b * F + f) * ldo + x] = T(fmaxf(a[j] + b2[f], 0.f) * s2[f] + t2[f]);
+        }
     }
 }
 
@@ -278,7 +297,7 @@ template int launch_attention<__half>(const __half*, int, const __half*, int, co
 template <class T>
 int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F, int P, T* out, int ldo,
                       cudaStream_t s) {
-    const size_t smem = sizeof(float) * (size_t)(p + F) * (P + 2);
+    const size_t smem = sizeof(float) * ((size_t)(p + F) * (P + 2) + (size_t)F * 3 * ((F + 3) & ~3));
     if (cudaFuncSetAttribute(prior_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -1;
     prior_conv_kernel<T><<<B, 256, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,

@@ -5,8 +5,9 @@
 // utils/data_utils.py:37 (F4a), model/ResNetSE34V2.py:96-98 (F4b).
 //
 // One CTA per clip, one warp per STFT frame (round-robin).  A frame is a 1024-point real
-// FFT done as a 512-point complex Stockham FFT in the warp's private shared-memory ping-pong
-// buffers (fp32, twiddles from a float64-built table), followed by the real-FFT untangling,
+// FFT done as a 512-point complex FFT: three radix-8 Stockham passes whose butterflies live in
+// registers (16 points per lane) and exchange through one padded, conflict-free shared-memory
+// buffer per warp (fp32, twiddles from a float64-built table), followed by the real-FFT untangling,
 // the sparse mel projection (<= 24 taps per mel) and the log.  The clip's (128, W) tile stays
 // in shared memory until the per-(clip, mel) statistics are known, so the audio is read once
 // and the log-mel written once: algorithmic HBM traffic 4*N + 4*128*W bytes per clip.
@@ -19,13 +20,17 @@ namespace {
 constexpr int kFFT = 1024;
 constexpr int kHalf = 512;       // complex FFT length
 constexpr int kHop = 512;
-constexpr int kBins = 513;
 constexpr int kMels = 128;
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
+constexpr int kBufLen = kHalf + kHalf / 8;     // padded: physical index i + (i >> 3)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)
+__device__ __forceinline__ int pad(int i) { return i + (i >> 3); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -38,6 +43,48 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// 8-point DFT in registers (forward, W8 = exp(-2 pi i / 8)): radix-2 DIT, y[u] = E[u & 3] +- W8^u O[u & 3]
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+    const float h = 0.70710678118654752f;
+    const float2 b0 = cadd(a[0], a[4]), b1 = csub(a[0], a[4]), b2 = cadd(a[2], a[6]), b3 = mul_mi(csub(a[2], a[6]));
+    const float2 b4 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]), b6 = cadd(a[3], a[7]), b7 = mul_mi(csub(a[3], a[7]));
+    const float2 c0 = cadd(b0, b2), c1 = cadd(b1, b3), c2 = csub(b0, b2), c3 = csub(b1, b3);
+    const float2 c4 = cadd(b4, b6), o1 = cadd(b5, b7), o2 = csub(b4, b6), o3 = csub(b5, b7);
+    const float2 c5 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));     // * (1 - i)/sqrt2
+    const float2 c6 = mul_mi(o2);                                            // * (-i)
+    const float2 c7 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));    // * (-1 - i)/sqrt2
+    a[0] = cadd(c0, c4); a[4] = csub(c0, c4);
+    a[1] = cadd(c1, c5); a[5] = csub(c1, c5);
+    a[2] = cadd(c2, c6); a[6] = csub(c2, c6);
+    a[3] = cadd(c3, c7); a[7] = csub(c3, c7);
+}
+
+// One Stockham radix-8 pass of the warp's 512-point FFT, in place: every lane reads the 16 points of its two
+// butterflies into registers, the warp synchronises, then the results go back in autosort order.
+//   in[j + 64 t] * W_{8 Ns}^{k t}  --DFT8-->  out[(j - k) * 8 + k + t * Ns],   k = j mod Ns
+template <int NS>
+__device__ __forceinline__ void fft_pass(float2* buf, int lane, const float2* __restrict__ tw512) {
+    float2 a[2][8];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const int j = lane + 32 * h2, k = j & (NS - 1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            a[h2][t] = buf[pad(j + 64 * t)];
+            if (NS > 1 && t > 0) a[h2][t] = cmul(a[h2][t], __ldg(&tw512[k * t * (64 / NS)]));
+        }
+        dft8(a[h2]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const int j = lane + 32 * h2, k = j & (NS - 1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) buf[pad((j - k) * 8 + k + t * NS)] = a[h2][t];
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int preemph,
               float* __restrict__ out, const float* __restrict__ window,
@@ -45,64 +92,60 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
               const int* __restrict__ mel_start, const int* __restrict__ mel_ptr,
               const float* __restrict__ mel_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                 // [kWarps][2][512]
-    float* tile = reinterpret_cast<float*>(fftbuf + kWarps * 2 * kHalf);  // [128][n_cols]
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                 // [kWarps][kBufLen]
+    float* tile = reinterpret_cast<float*>(fftbuf + kWarps * kBufLen);    // [128][n_cols]
     __shared__ float s_red[kWarps];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* x = audio + (size_t)blockIdx.x * N;
-    float2* buf0 = fftbuf + warp * 2 * kHalf;
-    float2* buf1 = buf0 + kHalf;
+    float2* buf = fftbuf + warp * kBufLen;
 
     for (int t = warp; t < n_cols; t += kWarps) {
-        // ---- framing + pre-emphasis + window; pack even/odd samples as one complex point ----
+        // ---- framing + pre-emphasis + window; even/odd samples of the frame form one complex point ----
         const int base = t * kHop - kFFT / 2;
+#pragma unroll 4
         for (int n = lane; n < kHalf; n += 32) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = 2 * n + e;
-                const int sidx = base + j;
-                float y = 0.f;
-                if (sidx >= 0 && sidx < N) {
-                    y = x[sidx];
-                    if (preemph) {
-                        const float prev = (sidx == 0) ? x[1] : x[sidx - 1];  // reflect pad of 1
-                        y = y - 0.97f * prev;
-                    }
-                }
-                v[e] = y * window[j];
+            const int s0 = base + 2 * n;
+            const float xm = (s0 - 1 >= 0 && s0 - 1 < N) ? x[s0 - 1] : 0.f;
+            float x0 = (s0 >= 0 && s0 < N) ? x[s0] : 0.f;
+            float x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? x[s0 + 1] : 0.f;
+            if (preemph) {
+                // y[t] = x[t] - 0.97 x[t-1], x[-1] := x[1] (reflect pad of 1); samples outside the clip stay zero
+                const float y1 = x1 - 0.97f * x0;
+                const float y0 = x0 - 0.97f * (s0 == 0 ? x[1] : xm);
+                x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? y1 : 0.f;
+                x0 = (s0 >= 0 && s0 < N) ? y0 : 0.f;
             }
-            buf0[n] = make_float2(v[0], v[1]);
+            const float2 w = *reinterpret_cast<const float2*>(window + 2 * n);
+            buf[pad(n)] = make_float2(x0 * w.x, x1 * w.y);
         }
         __syncwarp();
-        // ---- 512-point complex Stockham radix-2 FFT (9 passes) ----
-        float2* src = buf0;
-        float2* dst = buf1;
-#pragma unroll 1
-        for (int ns = 1; ns < kHalf; ns <<= 1) {
-            const int tw_stride = (kHalf / 2) / ns;
-            for (int j = lane; j < kHalf / 2; j += 32) {
-                const int k = j & (ns - 1);
-                const float2 a = src[j];
-                const float2 b = cmul(src[j + kHalf / 2], tw512[k * tw_stride]);
-                const int o = ((j - k) << 1) + k;
-                dst[o] = make_float2(a.x + b.x, a.y + b.y);
-                dst[o + ns] = make_float2(a.x - b.x, a.y - b.y);
+        // ---- 512-point complex FFT: three radix-8 Stockham passes ----
+        fft_pass<1>(buf, lane, tw512);
+        fft_pass<8>(buf, lane, tw512);
+        fft_pass<64>(buf, lane, tw512);
+        // ---- untangle to the 513-bin real spectrum; the power overwrites the buffer (513 floats) ----
+        float pw[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            const int k = lane + 32 * i;
+            pw[i] = 0.f;
+            if (k <= kHalf) {
+                const float2 zk = buf[pad(k & (kHalf - 1))];
+                const float2 zn = buf[pad((kHalf - k) & (kHalf - 1))];
+                const float2 ev = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                const float2 od = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+                const float2 r = cmul(od, __ldg(&tw1024[k]));
+                const float re = ev.x + r.x, im = ev.y + r.y;
+                pw[i] = re * re + im * im;
             }
-            __syncwarp();
-            float2* tmp = src; src = dst; dst = tmp;
         }
-        // ---- untangle to the 513-bin real spectrum, power in place of `dst` ----
-        float* power = reinterpret_cast<float*>(dst);          // 513 floats fit in 512 float2
-        for (int k = lane; k <= kHalf; k += 32) {
-            const float2 zk = src[k & (kHalf - 1)];
-            const float2 zn = src[(kHalf - k) & (kHalf - 1)];
-            const float2 ev = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-            const float2 od = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-            const float2 r = cmul(od, tw1024[k]);
-            const float re = ev.x + r.x, im = ev.y + r.y;
-            power[k] = re * re + im * im;
+        __syncwarp();
+        float* power = reinterpret_cast<float*>(buf);
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            const int k = lane + 32 * i;
+            if (k <= kHalf) power[k] = pw[i];
         }
         __syncwarp();
         // ---- sparse mel projection + log ----
@@ -153,7 +196,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
 
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
                   int preemph, float* out, cudaStream_t s) {
-    const size_t smem = sizeof(float2) * kWarps * 2 * kHalf + sizeof(float) * kMels * n_cols;
+    const size_t smem = sizeof(float2) * kWarps * kBufLen + sizeof(float) * kMels * n_cols;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
