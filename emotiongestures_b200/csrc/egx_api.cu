@@ -515,9 +515,13 @@ int debug_trunk_impl(egx_handle* h, const float* spec, int B, int stage, float* 
 // tensor-core arm: fp16 operands (NHWC fp16 trunk maps, fp16 GEMM A operands), fp32 accumulation,
 // fp32 residual stream / LayerNorm / outputs
 // ---------------------------------------------------------------------------------------------
+constexpr int kSeMaxC = 256;     // widest SE block (EmotionNet stage 4)
+
 struct TcSlots {
     __half *act[3], *down;
     float* se_sums;
+    __half* se_win;
+    float *se_mean, *se_gate;
     __half *fcin, *t16, *spec16, *pconv16, *prior16, *emo16, *fus16, *h0, *h1, *h2, *x16, *x1_16, *qkv16, *o16,
         *hid16, *enc16, *dec16, *post0, *post1, *post2;
     float *spec_feat, *prior_feat, *x32a, *x32b, *pre, *enc_out, *dec_out;
@@ -532,6 +536,9 @@ TcSlots plan_tc(const egx_handle* h, int B, Plan& p) {
     for (auto& a : s.act) a = p.take<__half>(map1);
     s.down = p.take<__half>(map2);
     s.se_sums = p.take<float>((size_t)B * (size_t)(h->H[0] * h->W[0] / 64 + 8) * 32);
+    s.se_win = p.take<__half>((size_t)B * 9 * kSeMaxC);
+    s.se_mean = p.take<float>((size_t)B * kSeMaxC);
+    s.se_gate = p.take<float>((size_t)B * 2 * kSeMaxC);
     const size_t R = (size_t)B * c.frames;
     const int hk = c.n_head * c.d_k, d = c.d_model;
     s.P8 = (c.pose_dim + 7) / 8 * 8;
@@ -579,7 +586,15 @@ int linear_tc(egx_handle* h, const LinearW& w, const __half* A, int lda, int M, 
 struct TrunkBufs {
     __half *act[3], *down;
     float* se_sums;
+    __half* se_win;              // [B][9*C] window means of conv1's output (fp16 GEMM operand)
+    float *se_mean, *se_gate;    // [B][C] mean of conv2's raw output; [B][2][C] folded gate
 };
+
+// EGX_SE_FUSED=0 (attribution experiments only) restores the separate gate*y + residual pass over the map
+bool se_fused() {
+    static const bool on = [] { const char* e = getenv("EGX_SE_FUSED"); return !e || atoi(e) != 0; }();
+    return on;
+}
 
 int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& blocks, int n_layers, int H0, int W0,
                  const float* spec, int B, const TrunkBufs& tb, int upto, __half** result, int* Hout, int* Wout,
@@ -599,6 +614,34 @@ int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& bl
         for (int b = 0; b < nblk[li]; ++b, ++bi) {
             const BlockW& bw = blocks[bi];
             const __half* res = x;
+            if (se_fused()) {
+                // SE gate ahead of conv2 (k_trunk.cu K4c/K4d): conv1 sums its output per tile, the window means go
+                // through conv2's own weights as a [B x 9C] x [9C x C] GEMM, and conv2's epilogue applies
+                // relu(g * BN(acc) + residual) directly: the block's output map is written once, y2 never exists
+                const int C = bw.conv2.cout;
+                if (C > kSeMaxC || bw.conv2.cin != C || bw.conv2.ks != 3 || bw.conv2.stride != 1) EGX_FAIL(h, "unsupported SE block geometry");
+                {
+                    StageScope sc(h, 3);
+                    LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, tb.se_sums, s));
+                    if (bw.has_down) {
+                        LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, tb.down, 0, nullptr, s));
+                        res = tb.down;
+                    }
+                }
+                {
+                    StageScope sc(h, 4);
+                    LAUNCH(h, launch_se_window(y, B, Ho, Wo, C, tb.se_sums,
+                                               conv_tc_tiles_per_clip(bw.conv1.cin, bw.conv1.cout, Ho, Wo), tb.se_win, s));
+                    LAUNCH(h, launch_gemm_tc(tb.se_win, 9 * C, bw.conv2.w16, 9 * C, B, C, 9 * C, GemmEpi{}, tb.se_mean, C, nullptr, 0, s));
+                    LAUNCH(h, launch_se_gate(bw.se, bw.conv2, tb.se_mean, B, tb.se_gate, s));
+                }
+                StageScope sc(h, 3);
+                LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, nullptr, s, tb.se_gate, res));
+                // rotate: the block's output z becomes x; the old x (the residual) is free again
+                __half* t = x; x = z; z = t;
+                Hc = Ho; Wc = Wo;
+                continue;
+            }
             {
                 StageScope sc(h, 3);
                 LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, nullptr, s));
@@ -622,7 +665,7 @@ int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& bl
 }
 
 int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto, __half** result, cudaStream_t s) {
-    TrunkBufs tb{{sl.act[0], sl.act[1], sl.act[2]}, sl.down, sl.se_sums};
+    TrunkBufs tb{{sl.act[0], sl.act[1], sl.act[2]}, sl.down, sl.se_sums, sl.se_win, sl.se_mean, sl.se_gate};
     int Ho, Wo;
     return run_trunk_tc(h, h->w.stem, h->w.blocks, 3, h->H[0], h->W[0], spec, B, tb, upto, result, &Ho, &Wo, s);
 }
@@ -998,6 +1041,9 @@ EmoSlots plan_emotion(int B, int H0, int W0, Plan& p) {
     for (auto& a : s.tb.act) a = p.take<__half>(map1);
     s.tb.down = p.take<__half>((size_t)B * ((H0 + 1) / 2) * ((W0 + 1) / 2) * 64);
     s.tb.se_sums = p.take<float>((size_t)B * (size_t)(H0 * W0 / 64 + 8) * 32);
+    s.tb.se_win = p.take<__half>((size_t)B * 9 * kSeMaxC);
+    s.tb.se_mean = p.take<float>((size_t)B * kSeMaxC);
+    s.tb.se_gate = p.take<float>((size_t)B * 2 * kSeMaxC);
     static const int dims[5] = {4096, 2048, 512, 128, 64};
     for (int i = 0; i < 5; ++i) s.fc[i] = p.take<__half>((size_t)B * dims[i]);
     return s;

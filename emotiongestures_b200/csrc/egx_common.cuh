@@ -213,6 +213,12 @@ template <class T>
 int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, int n_part, int B,
                     int HW, T* out, cudaStream_t s);
 
+// SE gate ahead of conv2 (tensor-core arm): window means of y1 (B,H,W,C) as fp16 rows [B][9*C], then the folded
+// per-clip epilogue of conv2, gate [B][2][C] = (g*scale2 | g*(shift2 + bias2*scale2)); see k_trunk.cu K4c/K4d
+int launch_se_window(const __half* y, int B, int H, int W, int C, const float* part, int n_part, __half* win,
+                     cudaStream_t s);
+int launch_se_gate(const SEW& se, const ConvW& conv2, const float* mean_raw, int B, float* gate, cudaStream_t s);
+
 struct GemmEpi {
     const float* bias = nullptr;      // [N]
     int relu = 0;
@@ -254,8 +260,10 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
 int conv_tc_init_device();
 // in: NHWC fp16 (B,Hin,Win,cin); out: NHWC fp16 or (B,cout,Ho*Wo) fp16 when nchw != 0
 // se_part (optional): [B][conv_tc_tiles_per_clip(Ho,Wo)][cout] per-tile channel sums (fixed order)
+// gate / res (optional, together): the epilogue becomes out = relu(acc * gate[b][0][c] + gate[b][1][c] + res), the
+// SE-scaled residual sum of Full_model/ResNetBlocks.py:28-36; res is NHWC fp16 with the output's geometry
 int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw,
-                   float* se_part, cudaStream_t s);
+                   float* se_part, cudaStream_t s, const float* gate = nullptr, const __half* res = nullptr);
 int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo);
 
 int attn_tc_init_device();

@@ -50,6 +50,8 @@ struct ConvTcParams {
     const float* shift;
     __half* out;           // NHWC (B,Ho,Wo,cout) or, if nchw, (B,cout,Ho*Wo)
     float* se_part;        // [B][tiles_h*tiles_w][cout] partial channel sums, or null
+    const float* gate;     // [B][2][ldc] folded SE epilogue (g*scale | g*shift) of the tile's clip, or null; with it
+    const __half* res;     // the residual map (output geometry, pitch ldc): out = relu(acc*gs + gb + res)
     int debug;             // EGX_CONV_DEBUG (attribution experiments only): 1 = no epilogue work, 2 = no TMA loads
 };
 
@@ -131,6 +133,35 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 32 fp16 channels (64 bytes) of one residual pixel
+struct Res32 { uint4 q[4]; };
+__device__ __forceinline__ void load_res32(Res32& r, const __half* p) {
+    // 256-bit loads: every 32-byte sector is requested by exactly one instruction
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r.q[2 * i].x), "=r"(r.q[2 * i].y), "=r"(r.q[2 * i].z), "=r"(r.q[2 * i].w),
+                       "=r"(r.q[2 * i + 1].x), "=r"(r.q[2 * i + 1].y), "=r"(r.q[2 * i + 1].z), "=r"(r.q[2 * i + 1].w)
+                     : "l"(p + 16 * i));
+}
+// v = relu(v * gs + gb + res) over one 32-channel chunk; gate_u32: shared-memory address of (gs[128] | gb[128])
+__device__ __forceinline__ void gated_residual32(float (&v)[32], uint32_t gate_u32, int nb, const Res32& r) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 sc = lds128(gate_u32 + (nb + 4 * j4) * 4);
+        const float4 sh = lds128(gate_u32 + (128 + nb + 4 * j4) * 4);
+        const uint4& q = r.q[j4 >> 1];
+        const uint32_t w0 = (j4 & 1) ? q.z : q.x, w1 = (j4 & 1) ? q.w : q.y;
+        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+        const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+        v[4 * j4] = fmaxf(fmaf(v[4 * j4], sc.x, sh.x) + r0.x, 0.f);
+        v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], sc.y, sh.y) + r0.y, 0.f);
+        v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], sc.z, sh.z) + r1.x, 0.f);
+        v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], sc.w, sh.w) + r1.y, 0.f);
+    }
 }
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
@@ -323,6 +354,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) { sc_r[j] = par[128 + j]; sh_r[j] = par[256 + j]; }
         }
+        const bool gated = p.gate != nullptr;     // SE-scaled residual epilogue (conv2 of a block)
+        Res32 rr = {};
         uint32_t tcount = grp, n_local = 0;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, tcount += 2, ++n_local) {
             const uint32_t b = fast_div((uint32_t)tile, p.magic_tpc);
@@ -333,6 +366,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool valid = in_patch && ho < p.Ho && wo < p.Wo;
             const uint32_t par_buf = n_local & 1;
             const uint32_t acc = tcount & 3;
+            // gated: everything that does not depend on the accumulator is requested before waiting for it
+            float g_s = 0.f, g_b = 0.f;
+            const __half* res_pix = nullptr;
+            if (gated) {
+                if (r < p.cout) {
+                    const float* gp = p.gate + (size_t)b * 2 * p.ldc + p.n_off + r;
+                    g_s = __ldg(gp);
+                    g_b = __ldg(gp + p.ldc);
+                }
+                if (valid && !(p.debug & 32)) {
+                    res_pix = p.res + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.ldc + p.n_off;
+                    load_res32(rr, res_pix);
+                }
+                const uint32_t nt = (uint32_t)tile + 2 * gridDim.x;      // this group's next tile: residual -> L2
+                if (nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
+                    const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * tiles_per_clip;
+                    const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
+                    const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    if (ho2 < p.Ho && wo2 < p.Wo) {
+                        const __half* np = p.res + (((size_t)b2 * p.Ho + ho2) * p.Wo + wo2) * p.ldc + p.n_off;
+                        prefetch_l2(np);
+                        if (NPAD > 64) prefetch_l2(np + 64);
+                    }
+                }
+            }
             mbar_wait(&tmem_full[acc], (tcount >> 2) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * S::kAccStride + ((uint32_t)(q * 32) << 16);
@@ -342,12 +400,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 continue;
             }
+            const uint32_t gate_u32 = red_u32 + par_buf * 512 * 4;     // (gs[128] | gb[128]) of this tile's clip
+            if (gated && !((p.debug & 128) && n_local >= 2)) {
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
+                named_bar_sync(1 + grp, 128);
+            }
 #pragma unroll 1
             for (int c = 0; c < (NPAD + 31) / 32; ++c) {
                 float v[32];
+                Res32 rn = {};
+                if (NPAD > 32 && gated && valid && c + 1 < (NPAD + 31) / 32 && !(p.debug & 32)) load_res32(rn, res_pix + (c + 1) * 32);
                 __syncwarp();
                 tmem_ld32(taddr + c * 32, v);
                 const int nb = c * 32;
+                if (gated) {
+                    gated_residual32(v, gate_u32, nb, rr);
+                    if (NPAD > 32) rr = rn;
+                } else {
                 if (has_bias) {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -375,6 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[4 * j4 + e] = fmaf(tv, sv[e], hv[e]);
                         }
                     }
+                }
                 }
                 if (OUT == OUT_TMA) {
                     if (in_patch) {
@@ -611,6 +682,8 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool se = p.se_part != nullptr;
         const uint32_t par_u32 = smem_u32(par);
         const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
+        const bool gated = p.gate != nullptr;     // SE-scaled residual epilogue (conv2 of a block)
+        Res32 rr = {};
         uint32_t n = 0;
         for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
             const uint32_t tile = 2 * u + grp;
@@ -620,28 +693,65 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool live = tile < (uint32_t)p.num_tiles;
             const bool valid = live && in_patch && ho < p.Ho && wo < p.Wo;
             const uint32_t buf = n & 1, par_buf = n & 1;
+            float g_s = 0.f, g_b = 0.f;
+            const __half* res_pix = nullptr;
+            if (gated) {
+                if (live) {
+                    const float* gp = p.gate + (size_t)b * 256 + r;
+                    g_s = __ldg(gp);
+                    g_b = __ldg(gp + 128);
+                }
+                if (valid && !(p.debug & 32)) {
+                    res_pix = p.res + (((size_t)b * p.Ho + ho) * p.Wo + wo) * 128;
+                    load_res32(rr, res_pix);
+                }
+                const uint32_t nt = 2 * (u + gridDim.x) + grp;            // this group's next tile: residual -> L2
+                if (nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
+                    const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * p.tiles_per_clip;
+                    const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
+                    const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    if (ho2 < p.Ho && wo2 < p.Wo) {
+                        const __half* np = p.res + (((size_t)b2 * p.Ho + ho2) * p.Wo + wo2) * 128;
+                        prefetch_l2(np);
+                        prefetch_l2(np + 64);
+                    }
+                }
+            }
             mbar_wait(&tmem_full[buf * 2 + grp], (n >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (buf * 2 + grp) * 128 + ((uint32_t)(q * 32) << 16);
             __half* o = p.out + (((size_t)b * p.Ho + ho) * p.Wo + wo) * 128;
+            const uint32_t gate_u32 = red_u32 + par_buf * 512 * 4;
+            if (gated) {
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
+                named_bar_sync(1 + grp, 128);
+            }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 float v[32];
+                Res32 rn = {};
+                if (gated && valid && c < 3 && !(p.debug & 32)) load_res32(rn, res_pix + (c + 1) * 32);
                 __syncwarp();
                 tmem_ld32(taddr + c * 32, v);
                 const int nb = c * 32;
+                if (gated) {
+                    gated_residual32(v, gate_u32, nb, rr);
+                    rr = rn;
+                } else {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 sc = lds128(par_u32 + (128 + nb + 4 * j4) * 4);
-                    const float4 sh = lds128(par_u32 + (256 + nb + 4 * j4) * 4);
-                    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_bias) bi = lds128(par_u32 + (nb + 4 * j4) * 4);
-                    const float sv[4] = {sc.x, sc.y, sc.z, sc.w}, hv[4] = {sh.x, sh.y, sh.z, sh.w}, bv[4] = {bi.x, bi.y, bi.z, bi.w};
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 sc = lds128(par_u32 + (128 + nb + 4 * j4) * 4);
+                        const float4 sh = lds128(par_u32 + (256 + nb + 4 * j4) * 4);
+                        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_bias) bi = lds128(par_u32 + (nb + 4 * j4) * 4);
+                        const float sv[4] = {sc.x, sc.y, sc.z, sc.w}, hv[4] = {sh.x, sh.y, sh.z, sh.w}, bv[4] = {bi.x, bi.y, bi.z, bi.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float tv = v[4 * j4 + e] + bv[e];
-                        if (relu_first) tv = fmaxf(tv, 0.f);
-                        v[4 * j4 + e] = fmaf(tv, sv[e], hv[e]);
+                        for (int e = 0; e < 4; ++e) {
+                            float tv = v[4 * j4 + e] + bv[e];
+                            if (relu_first) tv = fmaxf(tv, 0.f);
+                            v[4 * j4 + e] = fmaf(tv, sv[e], hv[e]);
+                        }
                     }
                 }
                 if (valid) {
@@ -715,11 +825,12 @@ void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
 
 int g_num_sms = 0;
 int g_debug = 0;
-int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too
+int g_out_direct = 5;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
 int g_halo = 7;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
-int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s) {
+int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s,
+               const float* gate, const __half* res) {
     using S = ConvCfg<CIN, NPAD, TAPS, HALO, OUT>;
     ConvTcParams p;
     p.ks = c.ks; p.stride = c.stride; p.pad = c.ks / 2;
@@ -738,6 +849,7 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     p.cout = c.cout - n_off < 128 ? c.cout - n_off : 128; p.n_off = n_off; p.ldc = c.cout; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
     p.out = out; p.se_part = se_part; p.debug = g_debug;
+    p.gate = gate; p.res = res;
 
     CUtensorMap ta, tb, to;
     const uint64_t dA[4] = {(uint64_t)CIN, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
@@ -769,7 +881,8 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, cudaStream_t s) {
+int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, cudaStream_t s,
+                   const float* gate, const __half* res) {
     ConvTcParams p;
     p.ks = 3; p.stride = 1; p.pad = 1;
     p.Ho = Hin; p.Wo = Win;
@@ -785,6 +898,7 @@ int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     p.cout = 128; p.n_off = 0; p.ldc = 128; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
     p.out = out; p.se_part = se_part; p.debug = g_debug;
+    p.gate = gate; p.res = res;
     CUtensorMap ta, tb;
     const uint64_t dA[4] = {128, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     const uint64_t sA[3] = {256, (uint64_t)Win * 256, (uint64_t)Hin * Win * 256};
@@ -847,18 +961,20 @@ int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo) {
 // in: NHWC fp16 (B,Hin,Win,cin).  out: NHWC fp16, or (B,cout,Ho*Wo) fp16 when nchw != 0.
 // se_part (optional): [B][tiles_per_clip][cout] per-tile channel sums of the fp32 outputs.
 int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, int nchw, float* se_part,
-                   cudaStream_t s) {
+                   cudaStream_t s, const float* gate, const __half* res) {
+    // the gated epilogue replaces conv2's own affine (folded into `gate`), shares shared memory with the SE sums
+    if ((gate != nullptr) != (res != nullptr) || (gate && (se_part || nchw || c.relu_first || c.cout % 32))) return -1;
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
     if ((c.cout > 128 && (nchw || c.cout % 128)) || (!nchw && c.cout % 32)) return -1;
     const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
-    if (halo && c.cin == 128) return launch_conv128(c, in, B, Hin, Win, out, se_part, s);
-    const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & 2))))) ? OUT_TMA : OUT_DIRECT);
+    if (halo && c.cin == 128) return launch_conv128(c, in, B, Hin, Win, out, se_part, s, gate, res);
+    const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & (gate ? 4 : 2)))))) ? OUT_TMA : OUT_DIRECT);
 #define X(CI, NP, TP, HL, OU)                                                                   \
     if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU)         \
     {                                                                                           \
         int n = 0;                                                                              \
         for (int n_off = 0; n_off < c.cout; n_off += 128) {                                     \
-            if (launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, n_off, s) < 0) return -1; \
+            if (launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, n_off, s, gate, res) < 0) return -1; \
             ++n;                                                                                \
         }                                                                                       \
         return n;                                                                               \

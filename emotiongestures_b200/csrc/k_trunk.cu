@@ -287,6 +287,115 @@ se_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, const float*
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4c/K4d  SE gate BEFORE conv2 runs (tensor-core arm).  The gate needs mean_{h,w}(BN2(conv2(y1))), and that
+// mean is linear in y1: for tap (ky,kx) of the zero-padded stride-1 3x3 conv2 the outputs read, in total, every
+// pixel of y1 except one border row and one border column, so
+//     mean(conv2(y1))[co] = (1/HW) * sum_{tap,ci} W2[co][tap][ci] * S_tap[ci],
+//     S_tap = T - R(excluded row) - C(excluded column) + y1(excluded row, excluded column),
+// with T the channel totals (summed by conv1's epilogue, fixed order), R / C border row / column sums.
+// K4c builds the nine window means per clip as one fp16 row [9*C] (the A operand of a small tensor-core GEMM
+// against conv2's own packed weights); K4d turns the GEMM result into the folded per-clip epilogue of conv2:
+//     out = relu(acc * (g*scale2) + (g*shift2) + residual),  g = sigmoid(W2 relu(W1 mean + b1) + b2)
+// (Full_model/ResNetBlocks.py:28-36,92-95).  conv2's output is never written unscaled and the separate
+// gate*y + residual pass over the map (3 map transfers per block) disappears.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_window_kernel(const __half* __restrict__ y, int H, int W, int C, const float* __restrict__ part, int n_part,
+                 __half* __restrict__ win) {
+    __shared__ float red[4][8][257];             // [class][channel-in-octet][thread]
+    __shared__ float cls[5][256];                // T, R0 (first row), RL (last row), C0 (first col), CL (last col)
+    const int b = blockIdx.x;
+    const int c8 = C / 8;                        // threads per pixel (8 channels = one 16-byte load each)
+    const int lanes = 256 / c8;                  // border pixels in flight
+    const int cq = threadIdx.x % c8, pl = threadIdx.x / c8;
+    const __half* img = y + (size_t)b * H * W * C;
+    float a[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[k][j] = 0.f;
+    const int n_border = 2 * W + 2 * H;
+    for (int i = pl; i < n_border; i += lanes) {
+        int k, hh, ww;
+        if (i < W) { k = 0; hh = 0; ww = i; }
+        else if (i < 2 * W) { k = 1; hh = H - 1; ww = i - W; }
+        else if (i < 2 * W + H) { k = 2; hh = i - 2 * W; ww = 0; }
+        else { k = 3; hh = i - 2 * W - H; ww = W - 1; }
+        const uint4 t = *reinterpret_cast<const uint4*>(img + ((size_t)hh * W + ww) * C + cq * 8);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            if (k == kk) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[kk][j] += v[j];
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[k][j][threadIdx.x] = a[k][j];
+    if (threadIdx.x < C) {
+        float t = 0.f;
+        for (int i = 0; i < n_part; ++i) t += part[((size_t)b * n_part + i) * C + threadIdx.x];
+        cls[0][threadIdx.x] = t;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 4 * C; o += 256) {
+        const int k = o / C, c = o % C;
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += red[k][c & 7][l * c8 + (c >> 3)];
+        cls[1 + k][c] = t;
+    }
+    __syncthreads();
+    const float inv = 1.f / (float)(H * W);
+    for (int o = threadIdx.x; o < 9 * C; o += 256) {
+        const int tap = o / C, c = o % C;
+        const int ky = tap / 3, kx = tap % 3;
+        float s = cls[0][c];
+        int er = -1, ec = -1;                                        // excluded row / column of y1
+        if (ky == 0) { s -= cls[2][c]; er = H - 1; } else if (ky == 2) { s -= cls[1][c]; er = 0; }
+        if (kx == 0) { s -= cls[4][c]; ec = W - 1; } else if (kx == 2) { s -= cls[3][c]; ec = 0; }
+        if (er >= 0 && ec >= 0) s += __half2float(img[((size_t)er * W + ec) * C + c]);
+        win[(size_t)b * 9 * C + o] = __float2half_rn(s * inv);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const float* __restrict__ mean_raw, int C, int R, const float* __restrict__ bias,
+               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w1,
+               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+               float* __restrict__ gate) {
+    __shared__ float mean[256], hid[32];
+    const int b = blockIdx.x, c = threadIdx.x;
+    float sc = 0.f, sh = 0.f;
+    if (c < C) {
+        sc = scale[c];
+        sh = shift[c] + (bias ? bias[c] * sc : 0.f);
+        mean[c] = fmaf(mean_raw[(size_t)b * C + c], sc, sh);
+    }
+    __syncthreads();
+    // hidden units: one warp each, lanes stride the channels (coalesced weight rows)
+    for (int j = c >> 5; j < R; j += blockDim.x >> 5) {
+        float t = 0.f;
+        for (int i = c & 31; i < C; i += 32) t = fmaf(w1[j * C + i], mean[i], t);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((c & 31) == 0) hid[j] = fmaxf(t + b1[j], 0.f);
+    }
+    __syncthreads();
+    if (c < C) {
+        float t = b2[c];
+        for (int j = 0; j < R; ++j) t = fmaf(w2[c * R + j], hid[j], t);
+        const float g = 1.f / (1.f + expf(-t));
+        gate[(size_t)b * 2 * C + c] = g * sc;
+        gate[(size_t)b * 2 * C + C + c] = g * sh;
+    }
+}
+
 template <class T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t total, int HW, int C,
                                     float* __restrict__ out) {
@@ -340,6 +449,20 @@ int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, 
     dim3 grid((HW + ppb - 1) / ppb, B);
     se_apply_kernel<T><<<grid, 256, 0, s>>>(y, res, sums, n_part, HW, se.c, se.r, se.w1, se.b1, se.w2,
                                             se.b2, ppb, out);
+    return ok() ? 1 : -1;
+}
+
+int launch_se_window(const __half* y, int B, int H, int W, int C, const float* part, int n_part, __half* win,
+                     cudaStream_t s) {
+    if (C % 8 || C > 256 || 256 % (C / 8)) return -1;
+    se_window_kernel<<<B, 256, 0, s>>>(y, H, W, C, part, n_part, win);
+    return ok() ? 1 : -1;
+}
+
+int launch_se_gate(const SEW& se, const ConvW& conv2, const float* mean_raw, int B, float* gate, cudaStream_t s) {
+    if (se.c > 256 || se.r > 32 || conv2.relu_first) return -1;
+    se_gate_kernel<<<B, 256, 0, s>>>(mean_raw, se.c, se.r, conv2.bias, conv2.scale, conv2.shift, se.w1, se.b1, se.w2,
+                                     se.b2, gate);
     return ok() ? 1 : -1;
 }
 
