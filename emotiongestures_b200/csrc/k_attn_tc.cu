@@ -76,6 +76,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 1) tmem_alloc<256>(tmem_ptr);
     // the padding key rows of V are never written by TMA but are read by the second MMA: they must be finite (x 0)
     for (int i = threadIdx.x; i < kKVBytes / 16; i += kAttnThreads) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0, 0, 0, 0);
+    // P is block diagonal and a row's clip never changes: everything outside a row's own key slot is zeroed ONCE
+    // here, the softmax below only ever rewrites the row's own LP columns
+    for (int i = threadIdx.x; i < kPBytes / 16; i += kAttnThreads) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -129,6 +132,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool row_used = r < rows;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         unsigned char* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+        // key columns any row of this warp needs (tcgen05.ld is warp-wide, so the window is the union of the warp's
+        // clips: 48 or 96 of the 144 columns for L = 34)
+        const int wr0 = q4 * 32, wr1 = min(q4 * 32 + 31, rows - 1);
+        const int w_lo = wr0 < rows ? (wr0 / p.L) * p.LP : 0;
+        const int w_hi = wr0 < rows ? (wr1 / p.L + 1) * p.LP : 0;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int g = tile / p.n_head, h = tile % p.n_head;
@@ -137,30 +145,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // pass 1: row maximum over the clip's own columns
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < p.NK; c += 32) {
-                float v[32];
+            for (int c = w_lo; c < w_hi; c += 16) {
+                float v[16];
                 __syncwarp();
-                tmem_ld32(tmem_S + lane_addr + c, v);
+                tmem_ld16(tmem_S + lane_addr + c, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < 16; ++j)
                     if (c + j >= c_lo && c + j < c_hi) mx = fmaxf(mx, v[j]);
             }
             // pass 2: p = exp((s - max) / sqrt(d_k)), zeros elsewhere, fp16 into the swizzled A-operand layout
             float sum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < p.NK; c += 32) {
-                float v[32];
+            for (int c = w_lo; c < w_hi; c += 16) {
+                float v[16];
                 __syncwarp();
-                tmem_ld32(tmem_S + lane_addr + c, v);
+                tmem_ld16(tmem_S + lane_addr + c, v);
+                if (!row_used || c < c_lo || c >= c_lo + p.LP) continue;      // not this row's key slot (16-aligned)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const bool own = row_used && c + j >= c_lo && c + j < c_hi;
-                    const float e = own ? exp2f((v[j] - mx) * p.scale_log2e) : 0.f;
+                for (int j = 0; j < 16; ++j) {
+                    const float e = c + j < c_hi ? exp2f((v[j] - mx) * p.scale_log2e) : 0.f;
                     v[j] = e;
                     sum += e;
                 }
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
+                for (int j8 = 0; j8 < 2; ++j8) {
                     const int chunk = (c >> 3) + j8;              // 16-byte chunk index along K
                     uint4 u;
                     *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j8], v[8 * j8 + 1]);

@@ -52,6 +52,8 @@ struct ConvTcParams {
     float* se_part;        // [B][tiles_h*tiles_w][cout] partial channel sums, or null
     const float* gate;     // [B][2][ldc] folded SE epilogue (g*scale | g*shift) of the tile's clip, or null; with it
     const __half* res;     // the residual map (output geometry, pitch ldc): out = relu(acc*gs + gb + res)
+    int contig;            // tile walk of a CTA: 1 = one contiguous run of tiles (consecutive tiles share a clip, so the
+                           // gated epilogue re-reads its per-clip gate rarely), 0 = blockIdx.x, +gridDim.x, ...
     int debug;             // EGX_CONV_DEBUG (attribution experiments only): 1 = no epilogue work, 2 = no TMA loads
 };
 
@@ -164,7 +166,39 @@ __device__ __forceinline__ void gated_residual32(float (&v)[32], uint32_t gate_u
     }
 }
 
-template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
+// same with the folded gate of all 32 channels in registers (cout = 32)
+__device__ __forceinline__ void gated_residual32_reg(float (&v)[32], const float (&gs)[32], const float (&gb)[32], const Res32& r) {
+#pragma unroll
+    for (int j2 = 0; j2 < 16; ++j2) {
+        const uint4& q = r.q[j2 >> 2];
+        const uint32_t w = (j2 & 3) == 0 ? q.x : ((j2 & 3) == 1 ? q.y : ((j2 & 3) == 2 ? q.z : q.w));
+        const float2 rv = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        v[2 * j2] = fmaxf(fmaf(v[2 * j2], gs[2 * j2], gb[2 * j2]) + rv.x, 0.f);
+        v[2 * j2 + 1] = fmaxf(fmaf(v[2 * j2 + 1], gs[2 * j2 + 1], gb[2 * j2 + 1]) + rv.y, 0.f);
+    }
+}
+
+// epilogue flavours
+enum { MODE_PLAIN = 0,    // y = BN([relu](acc + bias))
+       MODE_SE = 1,       // same, plus the per-tile channel sums of y (conv1 of an SE block)
+       MODE_GATED = 2 };  // out = relu(acc * gs + gb + residual) with the clip's folded SE gate (conv2 of an SE block)
+
+// tile walk of this CTA: tile(n) = t0 + n * tstep for n in [0, my_tiles)
+struct TileWalk { int t0, tstep, count; };
+__device__ __forceinline__ TileWalk tile_walk(int total, int contig) {
+    const int G = gridDim.x, c = blockIdx.x;
+    TileWalk w;
+    if (contig) {
+        w.t0 = (int)(((long long)c * total) / G);
+        w.tstep = 1;
+        w.count = (int)(((long long)(c + 1) * total) / G) - w.t0;
+    } else {
+        w.t0 = c; w.tstep = G; w.count = c < total ? (total - c + G - 1) / G : 0;
+    }
+    return w;
+}
+
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, ConvTcParams p) {
@@ -185,6 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_clip = p.tiles_per_clip;
     constexpr int KS = TAPS == 9 ? 3 : 1;
+    const TileWalk walk = tile_walk(p.num_tiles, p.contig);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -218,7 +253,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a_bytes = (uint32_t)p.BW * p.BH * S::kSwz;
             const uint32_t stage_tx = S::kKbPerStage * (a_bytes + (S::kResidentB ? 0u : (uint32_t)NPAD * S::kSwz));
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int n = 0; n < walk.count; ++n) {
+                const int tile = walk.t0 + n * walk.tstep;
                 const int b = tile / tiles_per_clip;
                 const int t = tile - b * tiles_per_clip;
                 const int wi0 = (t % p.tiles_w) * p.BW * p.stride - p.pad;
@@ -271,8 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t row_off[3] = {0u, (uint32_t)(p.MW * S::kSwz) >> 4, (uint32_t)(2 * p.MW * S::kSwz) >> 4};
             if (S::kResidentB) { mbar_wait(b_full, 0); tc_fence_after(); }
             constexpr uint32_t kStep = S::kTwoIssuers ? 2 : 1;
-            uint32_t tcount = S::kTwoIssuers ? issuer : 0;
-            for (int tile = blockIdx.x + tcount * gridDim.x; tile < p.num_tiles; tile += kStep * gridDim.x, tcount += kStep) {
+            for (uint32_t tcount = S::kTwoIssuers ? issuer : 0; (int)tcount < walk.count; tcount += kStep) {
                 uint32_t it = tcount * (HALO ? 1 : S::kStagesPerTile);
                 const uint32_t acc = tcount & 3;
                 mbar_wait(&tmem_empty[acc], ((tcount >> 2) & 1) ^ 1);
@@ -329,7 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int orow = ph_ * p.BW + pw_;        // row of the dense BH x BW output box
         const bool relu_first = p.relu_first != 0;
         const bool has_bias = p.bias != nullptr;
-        const bool se = p.se_part != nullptr;
+        constexpr bool se = MODE == MODE_SE, gated = MODE == MODE_GATED;
         const uint32_t par_u32 = smem_u32(par);
         const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
         // staging row of this thread with the TMA-store swizzle (16-byte chunk index XOR row bits)
@@ -349,15 +384,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             cp_dst[i] = (uint32_t)((cp_ph[i] * p.Wo + cp_pw[i]) * S::kOutRowBytes + ck * 16);
         }
         // NPAD == 32: the folded BatchNorm parameters of all channels live in registers
-        float sc_r[NPAD == 32 ? 32 : 1], sh_r[NPAD == 32 ? 32 : 1];
-        if (NPAD == 32) {
+        float sc_r[32], sh_r[32];      // only live for NPAD == 32
+        if (NPAD == 32 && !gated) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { sc_r[j] = par[128 + j]; sh_r[j] = par[256 + j]; }
         }
-        const bool gated = p.gate != nullptr;     // SE-scaled residual epilogue (conv2 of a block)
         Res32 rr = {};
-        uint32_t tcount = grp, n_local = 0;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, tcount += 2, ++n_local) {
+        // gated: the folded gate (gs | gb) of the clip being drained lives in registers (cout = 32) or in one of two
+        // shared-memory buffers of this group; it is re-read only when the clip changes
+        uint32_t cur_b = 0xffffffffu, gsel = 0;
+        uint32_t gate_u32 = red_u32;
+        for (uint32_t tcount = grp; (int)tcount < walk.count; tcount += 2) {
+            const uint32_t n_local = tcount >> 1;
+            const int tile = walk.t0 + (int)tcount * walk.tstep;
             const uint32_t b = fast_div((uint32_t)tile, p.magic_tpc);
             const uint32_t t = (uint32_t)tile - b * tiles_per_clip;
             const uint32_t th = fast_div(t, p.magic_tw);
@@ -367,20 +406,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t par_buf = n_local & 1;
             const uint32_t acc = tcount & 3;
             // gated: everything that does not depend on the accumulator is requested before waiting for it
-            float g_s = 0.f, g_b = 0.f;
             const __half* res_pix = nullptr;
             if (gated) {
-                if (r < p.cout) {
-                    const float* gp = p.gate + (size_t)b * 2 * p.ldc + p.n_off + r;
-                    g_s = __ldg(gp);
-                    g_b = __ldg(gp + p.ldc);
-                }
                 if (valid && !(p.debug & 32)) {
                     res_pix = p.res + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.ldc + p.n_off;
                     load_res32(rr, res_pix);
                 }
-                const uint32_t nt = (uint32_t)tile + 2 * gridDim.x;      // this group's next tile: residual -> L2
-                if (nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
+                if (b != cur_b) {                                        // uniform over the group
+                    cur_b = b;
+                    const float* gp = p.gate + (size_t)b * 2 * p.ldc + p.n_off;
+                    if (NPAD == 32) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(gp) + j4);
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(gp + p.ldc) + j4);
+                            sc_r[(4 * j4)] = a.x; sc_r[(4 * j4 + 1)] = a.y;
+                            sc_r[(4 * j4 + 2)] = a.z; sc_r[(4 * j4 + 3)] = a.w;
+                            sh_r[(4 * j4)] = c4.x; sh_r[(4 * j4 + 1)] = c4.y;
+                            sh_r[(4 * j4 + 2)] = c4.z; sh_r[(4 * j4 + 3)] = c4.w;
+                        }
+                    } else {
+                        gsel ^= 1;
+                        gate_u32 = red_u32 + gsel * 512 * 4;
+                        const float g_s = r < p.cout ? __ldg(gp + r) : 0.f, g_b = r < p.cout ? __ldg(gp + p.ldc + r) : 0.f;
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
+                        named_bar_sync(1 + grp, 128);
+                    }
+                }
+                const uint32_t nt = (uint32_t)tile + 2 * walk.tstep;      // this group's next tile: residual -> L2
+                if ((int)tcount + 2 < walk.count && in_patch && !(p.debug & 64)) {
                     const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * tiles_per_clip;
                     const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
                     const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
@@ -400,12 +455,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 continue;
             }
-            const uint32_t gate_u32 = red_u32 + par_buf * 512 * 4;     // (gs[128] | gb[128]) of this tile's clip
-            if (gated && !((p.debug & 128) && n_local >= 2)) {
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
-                named_bar_sync(1 + grp, 128);
-            }
 #pragma unroll 1
             for (int c = 0; c < (NPAD + 31) / 32; ++c) {
                 float v[32];
@@ -415,7 +464,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld32(taddr + c * 32, v);
                 const int nb = c * 32;
                 if (gated) {
-                    gated_residual32(v, gate_u32, nb, rr);
+                    if (NPAD == 32) gated_residual32_reg(v, sc_r, sh_r, rr);
+                    else gated_residual32(v, gate_u32, nb, rr);
                     if (NPAD > 32) rr = rn;
                 } else {
                 if (has_bias) {
@@ -561,6 +611,7 @@ struct C128 {
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvTcParams p) {
     using S = C128;
@@ -576,7 +627,7 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* par = reinterpret_cast<float*>(smem + S::kParOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_super = (p.num_tiles + 1) >> 1;
+    const TileWalk walk = tile_walk((p.num_tiles + 1) >> 1, p.contig);     // over super-tiles (pairs of tiles)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -602,8 +653,9 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ================= TMA producer =================
         if (elect_one()) {
             const uint32_t a_tx = (uint32_t)p.MW * (p.BH + 2) * 128;
-            uint32_t it = 0, n = 0;
-            for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+            uint32_t it = 0;
+            for (uint32_t n = 0; (int)n < walk.count; ++n) {
+                const int u = walk.t0 + (int)n * walk.tstep;
                 int wi0[2], hi0[2], bb[2];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
@@ -640,8 +692,8 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem + S::kBOffset));
             const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + S::kAOffset + t * 2 * S::kPatchBytes));
             const uint32_t row_off[3] = {0u, (uint32_t)(p.MW * 128) >> 4, (uint32_t)(2 * p.MW * 128) >> 4};
-            uint32_t it = 0, n = 0;
-            for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+            uint32_t it = 0;
+            for (uint32_t n = 0; (int)n < walk.count; ++n) {
                 const uint32_t buf = n & 1;
                 mbar_wait(&tmem_empty[buf * 2 + t], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -679,13 +731,14 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool in_patch = ph_ < p.BH && pw_ < p.BW;
         const bool relu_first = p.relu_first != 0;
         const bool has_bias = p.bias != nullptr;
-        const bool se = p.se_part != nullptr;
+        constexpr bool se = MODE == MODE_SE, gated = MODE == MODE_GATED;
         const uint32_t par_u32 = smem_u32(par);
         const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
-        const bool gated = p.gate != nullptr;     // SE-scaled residual epilogue (conv2 of a block)
         Res32 rr = {};
-        uint32_t n = 0;
-        for (int u = blockIdx.x; u < n_super; u += gridDim.x, ++n) {
+        uint32_t cur_b = 0xffffffffu, gsel = 0;      // clip whose folded gate sits in shared-memory buffer gsel
+        uint32_t gate_u32 = red_u32;
+        for (uint32_t n = 0; (int)n < walk.count; ++n) {
+            const int u = walk.t0 + (int)n * walk.tstep;
             const uint32_t tile = 2 * u + grp;
             const uint32_t b = fast_div(tile, p.magic_tpc), tt = tile - b * p.tiles_per_clip;
             const uint32_t th = fast_div(tt, p.magic_tw), tw = tt - th * p.tiles_w;
@@ -693,20 +746,24 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool live = tile < (uint32_t)p.num_tiles;
             const bool valid = live && in_patch && ho < p.Ho && wo < p.Wo;
             const uint32_t buf = n & 1, par_buf = n & 1;
-            float g_s = 0.f, g_b = 0.f;
             const __half* res_pix = nullptr;
             if (gated) {
-                if (live) {
-                    const float* gp = p.gate + (size_t)b * 256 + r;
-                    g_s = __ldg(gp);
-                    g_b = __ldg(gp + 128);
-                }
                 if (valid && !(p.debug & 32)) {
                     res_pix = p.res + (((size_t)b * p.Ho + ho) * p.Wo + wo) * 128;
                     load_res32(rr, res_pix);
                 }
-                const uint32_t nt = 2 * (u + gridDim.x) + grp;            // this group's next tile: residual -> L2
-                if (nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
+                if (live && b != cur_b) {                                 // uniform over the group
+                    cur_b = b;
+                    gsel ^= 1;
+                    gate_u32 = red_u32 + gsel * 512 * 4;
+                    const float* gp = p.gate + (size_t)b * 256 + r;
+                    const float g_s = __ldg(gp), g_b = __ldg(gp + 128);
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
+                    named_bar_sync(1 + grp, 128);
+                }
+                const uint32_t nt = 2 * (u + walk.tstep) + grp;           // this group's next tile: residual -> L2
+                if ((int)n + 1 < walk.count && nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
                     const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * p.tiles_per_clip;
                     const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
                     const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
@@ -721,12 +778,6 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + (buf * 2 + grp) * 128 + ((uint32_t)(q * 32) << 16);
             __half* o = p.out + (((size_t)b * p.Ho + ho) * p.Wo + wo) * 128;
-            const uint32_t gate_u32 = red_u32 + par_buf * 512 * 4;
-            if (gated) {
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + r * 4), "f"(g_s) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(gate_u32 + (128 + r) * 4), "f"(g_b) : "memory");
-                named_bar_sync(1 + grp, 128);
-            }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 float v[32];
@@ -825,10 +876,11 @@ void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
 
 int g_num_sms = 0;
 int g_debug = 0;
-int g_out_direct = 5;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
+int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
+int g_contig = 0;    // EGX_CONV_CONTIG: 1 = contiguous tile runs per CTA, 0 = strided walk (default: measured faster, the CTAs share halos in L2)
 int g_halo = 7;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
 
-template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT, int MODE>
 int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s,
                const float* gate, const __half* res) {
     using S = ConvCfg<CIN, NPAD, TAPS, HALO, OUT>;
@@ -849,7 +901,7 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     p.cout = c.cout - n_off < 128 ? c.cout - n_off : 128; p.n_off = n_off; p.ldc = c.cout; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
     p.out = out; p.se_part = se_part; p.debug = g_debug;
-    p.gate = gate; p.res = res;
+    p.gate = gate; p.res = res; p.contig = g_contig;
 
     CUtensorMap ta, tb, to;
     const uint64_t dA[4] = {(uint64_t)CIN, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
@@ -877,7 +929,7 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
         to = ta;
     }
     const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-    conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, to, p);
+    conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT, MODE><<<grid, kConvThreads, S::kTotal, s>>>(ta, tb, to, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -898,7 +950,7 @@ int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     p.cout = 128; p.n_off = 0; p.ldc = 128; p.relu_first = c.relu_first;
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift;
     p.out = out; p.se_part = se_part; p.debug = g_debug;
-    p.gate = gate; p.res = res;
+    p.gate = gate; p.res = res; p.contig = g_contig;
     CUtensorMap ta, tb;
     const uint64_t dA[4] = {128, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
     const uint64_t sA[3] = {256, (uint64_t)Win * 256, (uint64_t)Hin * Win * 256};
@@ -910,13 +962,15 @@ int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     const int n_super = (p.num_tiles + 1) / 2;
     const int grid = n_super < g_num_sms ? n_super : g_num_sms;
-    conv128_tc_kernel<<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
+    if (gate) conv128_tc_kernel<MODE_GATED><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
+    else if (se_part) conv128_tc_kernel<MODE_SE><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
+    else conv128_tc_kernel<MODE_PLAIN><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-template <int CIN, int NPAD, int TAPS, bool HALO, int OUT>
+template <int CIN, int NPAD, int TAPS, bool HALO, int OUT, int MODE>
 int set_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(conv_tc_kernel<CIN, NPAD, TAPS, HALO, OUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ConvCfg<CIN, NPAD, TAPS, HALO, OUT>::kTotal) == cudaSuccess ? 0 : -1;
 }
 
@@ -931,6 +985,18 @@ int set_attr() {
     X(256, 128, 9, false, OUT_DIRECT) X(128, 128, 1, false, OUT_DIRECT)                               \
     X(128, 48, 9, false, OUT_NCHW) X(128, 64, 9, false, OUT_NCHW)
 
+// conv1 of an SE block (sums its output): stride-1 halo kernels, the stride-2 first blocks of a stage, 256-wide slices
+#define EGX_CONV_SE_INSTANCES(X)                                                                       \
+    X(32, 32, 9, true, OUT_TMA) X(32, 32, 9, false, OUT_TMA) X(64, 64, 9, true, OUT_TMA)              \
+    X(64, 64, 9, false, OUT_TMA) X(32, 64, 9, false, OUT_TMA) X(64, 128, 9, false, OUT_DIRECT)        \
+    X(128, 128, 9, false, OUT_DIRECT) X(32, 32, 9, true, OUT_DIRECT) X(64, 64, 9, true, OUT_DIRECT)   \
+    X(256, 128, 9, false, OUT_DIRECT)
+// conv2 of an SE block (gated residual epilogue): always cin == cout, stride 1
+#define EGX_CONV_GATED_INSTANCES(X)                                                                    \
+    X(32, 32, 9, true, OUT_TMA) X(32, 32, 9, false, OUT_TMA) X(64, 64, 9, true, OUT_TMA)              \
+    X(64, 64, 9, false, OUT_TMA) X(128, 128, 9, false, OUT_DIRECT) X(32, 32, 9, true, OUT_DIRECT)     \
+    X(64, 64, 9, true, OUT_DIRECT) X(256, 128, 9, false, OUT_DIRECT)
+
 int conv_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -938,9 +1004,19 @@ int conv_tc_init_device() {
     if (const char* e = getenv("EGX_CONV_HALO")) g_halo = atoi(e);
     if (const char* e = getenv("EGX_CONV_DEBUG")) g_debug = atoi(e);
     if (const char* e = getenv("EGX_CONV_OUT")) g_out_direct = atoi(e);
-    int rc = cudaFuncSetAttribute(conv128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
-#define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU>();
+    if (const char* e = getenv("EGX_CONV_CONTIG")) g_contig = atoi(e);
+    int rc = 0;
+    rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
+    rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
+    rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
+#define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU, MODE_PLAIN>();
     EGX_CONV_INSTANCES(X)
+#undef X
+#define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU, MODE_SE>();
+    EGX_CONV_SE_INSTANCES(X)
+#undef X
+#define X(CI, NP, TP, HL, OU) rc |= set_attr<CI, NP, TP, HL, OU, MODE_GATED>();
+    EGX_CONV_GATED_INSTANCES(X)
 #undef X
     return rc;
 }
@@ -969,18 +1045,27 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
     if (halo && c.cin == 128) return launch_conv128(c, in, B, Hin, Win, out, se_part, s, gate, res);
     const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & (gate ? 4 : 2)))))) ? OUT_TMA : OUT_DIRECT);
-#define X(CI, NP, TP, HL, OU)                                                                   \
-    if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU)         \
+#define X_MODE(CI, NP, TP, HL, OU, MD)                                                          \
+    if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU && mode == MD) \
     {                                                                                           \
         int n = 0;                                                                              \
         for (int n_off = 0; n_off < c.cout; n_off += 128) {                                     \
-            if (launch_one<CI, NP, TP, HL, OU>(c, in, B, Hin, Win, out, se_part, n_off, s, gate, res) < 0) return -1; \
+            if (launch_one<CI, NP, TP, HL, OU, MD>(c, in, B, Hin, Win, out, se_part, n_off, s, gate, res) < 0) return -1; \
             ++n;                                                                                \
         }                                                                                       \
         return n;                                                                               \
     }
+    const int mode = gate ? MODE_GATED : (se_part ? MODE_SE : MODE_PLAIN);
+#define X(CI, NP, TP, HL, OU) X_MODE(CI, NP, TP, HL, OU, MODE_PLAIN)
     EGX_CONV_INSTANCES(X)
 #undef X
+#define X(CI, NP, TP, HL, OU) X_MODE(CI, NP, TP, HL, OU, MODE_SE)
+    EGX_CONV_SE_INSTANCES(X)
+#undef X
+#define X(CI, NP, TP, HL, OU) X_MODE(CI, NP, TP, HL, OU, MODE_GATED)
+    EGX_CONV_GATED_INSTANCES(X)
+#undef X
+#undef X_MODE
     return -1;
 }
 

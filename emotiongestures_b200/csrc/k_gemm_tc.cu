@@ -10,8 +10,15 @@
 //   warp 1    single-thread tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
 //   warps 2-9 two epilogue groups (even / odd tiles), one accumulator row per thread
 // K tails and M/N tails come from TMA zero fill; stores are predicated.
+//
+// RES variant (weights resident): with M = B*F >> N and K = d = 256 a 128 x 256 tile streams 192 KB from L2 for only
+// 16.8 MFLOP, and 148 SMs doing that saturate the L2 (measured: 390 TFLOP/s on the QKV projection).  When the CTA's
+// [BN x K] weight slice fits (<= 160 KB) it is loaded ONCE, the CTA keeps its n-slice and walks down the m-tiles, and
+// only the 16 KB A blocks go through the ring: L2 traffic per tile drops 3x.
 #include "egx_common.cuh"
 #include "tc_common.cuh"
+
+#include <cstdlib>
 
 namespace egx {
 
@@ -23,16 +30,46 @@ constexpr int GM = 128;          // tile rows (UMMA M)
 constexpr int GK = 64;           // fp16 elements per K block = one 128-byte swizzle row
 constexpr int kGemmThreads = 320;
 
-template <int BN>
+constexpr int kResMaxBytes = 160 * 1024;    // resident weight slice of the RES variant
+
+template <int BN, bool RES>
 struct GemmCfg {
     static constexpr int kABytes = GM * GK * 2;
     static constexpr int kBBytes = BN * GK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = BN == 256 ? 4 : 6;
-    static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 256 + 1024;
+    static constexpr int kStageBytes = RES ? kABytes : kABytes + kBBytes;
+    static constexpr int kStages = RES ? 4 : (BN == 256 ? 4 : 6);
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    // layout: [resident B: num_kb * kBBytes (RES only)] [ring] [barriers]
+    static constexpr int total(int num_kb) { return (RES ? num_kb * kBBytes : 0) + kRingBytes + 256 + 1024; }
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
+
+// tile i of this CTA -> (m0, n0)
+struct GemmWalk { int m_first, m_step, n0, count, n_tiles; };
+template <int BN, bool RES>
+__device__ __forceinline__ GemmWalk gemm_walk(int M, int N) {
+    const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + GM - 1) / GM, G = gridDim.x, c = blockIdx.x;
+    GemmWalk w;
+    w.n_tiles = n_tiles;
+    if (RES) {                                   // grid is a multiple of n_tiles
+        const int per = G / n_tiles;
+        w.n0 = (c % n_tiles) * BN;
+        w.m_first = c / n_tiles;
+        w.m_step = per;
+        w.count = w.m_first < m_tiles ? (m_tiles - w.m_first + per - 1) / per : 0;
+    } else {
+        const int total = m_tiles * n_tiles;
+        w.n0 = 0; w.m_first = c; w.m_step = G;
+        w.count = c < total ? (total - c + G - 1) / G : 0;
+    }
+    return w;
+}
+template <int BN, bool RES>
+__device__ __forceinline__ void gemm_tile(const GemmWalk& w, int i, int* m0, int* n0) {
+    const int t = w.m_first + i * w.m_step;
+    if (RES) { *m0 = t * GM; *n0 = w.n0; }
+    else { *m0 = (t / w.n_tiles) * GM; *n0 = (t % w.n_tiles) * BN; }
+}
 
 struct GemmTcEpi {
     const float* bias;
@@ -43,29 +80,31 @@ struct GemmTcEpi {
     __half* out16; int ld16;
 };
 
-template <int BN>
+template <int BN, bool RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int K, GemmTcEpi ep) {
-    using S = GemmCfg<BN>;
+    using S = GemmCfg<BN, RES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+    const int num_kb = (K + GK - 1) / GK;
+    unsigned char* ring = smem + (RES ? num_kb * S::kBBytes : 0);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + S::kRingBytes);
     uint64_t* empty = full + S::kStages;
     uint64_t* tmem_full = empty + S::kStages;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* b_full = tmem_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (K + GK - 1) / GK;
-    const int n_tiles = (N + BN - 1) / BN;
-    const int num_tiles = ((M + GM - 1) / GM) * n_tiles;
+    const GemmWalk walk = gemm_walk<BN, RES>(M, N);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int i = 0; i < S::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        mbar_init(b_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<S::kTmemCols>(tmem_ptr);
@@ -76,16 +115,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
+            if (RES && walk.count > 0) {
+                mbar_expect_tx(b_full, (uint32_t)num_kb * S::kBBytes);
+                for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem + kb * S::kBBytes, &tmB, b_full, kb * GK, walk.n0);
+            }
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * BN;
+            for (int i = 0; i < walk.count; ++i) {
+                int m0, n0;
+                gemm_tile<BN, RES>(walk, i, &m0, &n0);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int st = it % S::kStages;
                     mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
-                    unsigned char* a = smem + st * S::kStageBytes;
+                    unsigned char* a = ring + st * S::kStageBytes;
                     mbar_expect_tx(&full[st], S::kStageBytes);
                     tma_load_2d(a, &tmA, &full[st], kb * GK, m0);
-                    tma_load_2d(a + S::kABytes, &tmB, &full[st], kb * GK, n0);
+                    if (!RES) tma_load_2d(a + S::kABytes, &tmB, &full[st], kb * GK, n0);
                 }
             }
         }
@@ -93,8 +137,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GM, BN);
             constexpr uint32_t kDescHi = smem_desc_hi<128>();
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            uint32_t it = 0;
+            const uint32_t res_lo = smem_desc_lo(smem_u32(smem));
+            if (RES && walk.count > 0) { mbar_wait(b_full, 0); tc_fence_after(); }
+            for (uint32_t tcount = 0; (int)tcount < walk.count; ++tcount) {
                 const uint32_t acc = tcount & 1;
                 mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -103,15 +149,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int st = it % S::kStages;
                     mbar_wait(&full[st], (it / S::kStages) & 1);
                     tc_fence_after();
-                    const uint32_t a_lo = smem_desc_lo(smem_u32(smem + st * S::kStageBytes));
+                    const uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * S::kStageBytes));
+                    const uint32_t b_lo = RES ? res_lo + ((kb * S::kBBytes) >> 4) : a_lo + (S::kABytes >> 4);
                     if (kb == 0) {
 #pragma unroll
-                        for (int k = 0; k < GK / 16; ++k)
-                            umma_f16_lo<kDescHi>(d, a_lo + 2 * k, a_lo + (S::kABytes >> 4) + 2 * k, idesc, k != 0);
+                        for (int k = 0; k < GK / 16; ++k) umma_f16_lo<kDescHi>(d, a_lo + 2 * k, b_lo + 2 * k, idesc, k != 0);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < GK / 16; ++k)
-                            umma_f16_lo<kDescHi>(d, a_lo + 2 * k, a_lo + (S::kABytes >> 4) + 2 * k, idesc, true);
+                        for (int k = 0; k < GK / 16; ++k) umma_f16_lo<kDescHi>(d, a_lo + 2 * k, b_lo + 2 * k, idesc, true);
                     }
                     umma_commit(&empty[st]);
                 }
@@ -124,9 +169,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = q * 32 + lane;
         const bool relu = ep.relu != 0;
         const bool add_vec = (ep.addend_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.addend) & 15) == 0;
-        uint32_t tcount = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, tcount += 2) {
-            const int m = (tile / n_tiles) * GM + row, n0 = (tile % n_tiles) * BN;
+        for (uint32_t tcount = grp; (int)tcount < walk.count; tcount += 2) {
+            int m0, n0;
+            gemm_tile<BN, RES>(walk, (int)tcount, &m0, &n0);
+            const int m = m0 + row;
             mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
             tc_fence_after();
             const float* add_row = nullptr;
@@ -175,7 +221,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (ep.out32) {
                         float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
-                        if (full_chunk && (ep.ld32 & 3) == 0) {
+                        if (full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0) {
+                            // 256-bit stores: every instruction writes whole 32-byte sectors
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8 * j),
+                                             "f"(v[8 * j]), "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]),
+                                             "f"(v[8 * j + 4]), "f"(v[8 * j + 5]), "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
+                                             : "memory");
+                        } else if (full_chunk && (ep.ld32 & 3) == 0) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 reinterpret_cast<float4*>(o)[j] =
@@ -188,7 +242,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (ep.out16) {
                         __half* o = ep.out16 + (size_t)m * ep.ld16 + nb;
-                        if (full_chunk && (ep.ld16 & 7) == 0) {
+                        if (full_chunk && (ep.ld16 & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out16) & 31) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                uint32_t u[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const __half2 h2 = __floats2half2_rn(v[16 * j + 2 * e], v[16 * j + 2 * e + 1]);
+                                    u[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 16 * j),
+                                             "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                                             : "memory");
+                            }
+                        } else if (full_chunk && (ep.ld16 & 7) == 0) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint4 u;
@@ -227,8 +294,9 @@ __global__ void cvt_pad_kernel(const float* __restrict__ in, int64_t rows, int c
 }
 
 int g_gemm_sms = 0;
+int g_gemm_res = 1;      // EGX_GEMM_RES=0 (attribution experiments only): never keep the weight slice resident
 
-template <int BN>
+template <int BN, bool RES>
 int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmTcEpi& ep,
               cudaStream_t s) {
     CUtensorMap ta, tb;
@@ -237,9 +305,10 @@ int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, 
     const uint32_t bA[2] = {GK, GM}, bB[2] = {GK, BN};
     if (!make_tmap_f16(&ta, A, 2, dA, sA, bA, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     if (!make_tmap_f16(&tb, W, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
-    const int grid = tiles < g_gemm_sms ? tiles : g_gemm_sms;
-    gemm_tc_kernel<BN><<<grid, kGemmThreads, GemmCfg<BN>::kTotal, s>>>(ta, tb, M, N, K, ep);
+    const int n_tiles = (N + BN - 1) / BN, tiles = ((M + GM - 1) / GM) * n_tiles;
+    int grid = tiles < g_gemm_sms ? tiles : g_gemm_sms;
+    if (RES) grid = grid / n_tiles * n_tiles;          // every CTA keeps one n-slice
+    gemm_tc_kernel<BN, RES><<<grid, kGemmThreads, GemmCfg<BN, RES>::total((K + GK - 1) / GK), s>>>(ta, tb, M, N, K, ep);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -250,10 +319,14 @@ int gemm_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<128>::kTotal) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<256>::kTotal) != cudaSuccess) return -1;
+    if (const char* e = getenv("EGX_GEMM_RES")) g_gemm_res = atoi(e);
+    const int res_max = kResMaxBytes + GemmCfg<128, true>::total(0);
+    if (cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<128, false>::total(0)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GemmCfg<256, false>::total(0)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -269,8 +342,18 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
     GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16};
-    if (N % 256 == 0) return launch_bn<256>(A, lda, W, ldw, M, N, K, ep, s);
-    return launch_bn<128>(A, lda, W, ldw, M, N, K, ep, s);
+    const int num_kb = (K + GK - 1) / GK;
+    const int m_tiles = (M + GM - 1) / GM;
+    // weights resident when the slice fits and every CTA gets several m-tiles to amortise loading it
+    if (g_gemm_res) {
+        if (N % 256 == 0 && num_kb * GemmCfg<256, true>::kBBytes <= kResMaxBytes && (long)m_tiles * (N / 256) >= 4L * g_gemm_sms)
+            return launch_bn<256, true>(A, lda, W, ldw, M, N, K, ep, s);
+        const int n128 = (N + 127) / 128;
+        if (num_kb * GemmCfg<128, true>::kBBytes <= kResMaxBytes && (long)m_tiles * n128 >= 4L * g_gemm_sms && n128 <= g_gemm_sms)
+            return launch_bn<128, true>(A, lda, W, ldw, M, N, K, ep, s);
+    }
+    if (N % 256 == 0) return launch_bn<256, false>(A, lda, W, ldw, M, N, K, ep, s);
+    return launch_bn<128, false>(A, lda, W, ldw, M, N, K, ep, s);
 }
 
 }  // namespace egx

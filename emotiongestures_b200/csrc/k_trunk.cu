@@ -70,6 +70,14 @@ stem_kernel(const float* __restrict__ spec, int H, int W, const float* __restric
         for (int k = 0; k < 9; ++k) wr[j][k] = w[c * 9 + k];
         br[j] = bias[c]; sr[j] = scale[c]; tr[j] = shift[c];
     }
+    // pin the 96 parameters in registers: without this the compiler re-reads them from global memory inside the
+    // pixel loop (one LDG per FMA) instead of keeping them live
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) asm volatile("" : "+f"(wr[j][k]));
+        asm volatile("" : "+f"(br[j]), "+f"(sr[j]), "+f"(tr[j]));
+    }
     __syncthreads();
     const int rows = min(kStemRows, H - y0);
     for (int pix = threadIdx.x >> 2; pix < rows * W; pix += blockDim.x >> 2) {
@@ -303,52 +311,49 @@ se_apply_kernel(const T* __restrict__ y, const T* __restrict__ res, const float*
 __global__ void __launch_bounds__(256)
 se_window_kernel(const __half* __restrict__ y, int H, int W, int C, const float* __restrict__ part, int n_part,
                  __half* __restrict__ win) {
-    __shared__ float red[4][8][257];             // [class][channel-in-octet][thread]
+    __shared__ float red[4][64][9];              // [class][thread of the class][channel in octet] (padded)
     __shared__ float cls[5][256];                // T, R0 (first row), RL (last row), C0 (first col), CL (last col)
+    __shared__ float tot[8][256];                // [slice][channel] partial totals (256 / C slices, C >= 32)
     const int b = blockIdx.x;
-    const int c8 = C / 8;                        // threads per pixel (8 channels = one 16-byte load each)
-    const int lanes = 256 / c8;                  // border pixels in flight
-    const int cq = threadIdx.x % c8, pl = threadIdx.x / c8;
     const __half* img = y + (size_t)b * H * W * C;
-    float a[4][8];
+    // tile totals: 256 / C slices of the partials per channel (summed over the slices in a fixed order below)
+    {
+        const int c = threadIdx.x % C, sl = threadIdx.x / C, nsl = 256 / C;
+        float t = 0.f;
+#pragma unroll 4
+        for (int i = sl; i < n_part; i += nsl) t += part[((size_t)b * n_part + i) * C + c];
+        tot[sl][c] = t;
+    }
+    // border sums: 64 threads per class (first row, last row, first column, last column); inside a class C/8 threads
+    // cover one pixel (16-byte loads) and 512/C pixels are in flight
+    const int k = threadIdx.x >> 6, tk = threadIdx.x & 63;
+    const int c8 = C / 8, lanes = 64 / c8;
+    const int cq = tk % c8, pl = tk / c8;
+    const int n_pix = k < 2 ? W : H;
+    const size_t base = k == 0 ? 0 : (k == 1 ? (size_t)(H - 1) * W * C : (k == 2 ? 0 : (size_t)(W - 1) * C));
+    const size_t pitch = k < 2 ? (size_t)C : (size_t)W * C;
+    float a[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[k][j] = 0.f;
-    const int n_border = 2 * W + 2 * H;
-    for (int i = pl; i < n_border; i += lanes) {
-        int k, hh, ww;
-        if (i < W) { k = 0; hh = 0; ww = i; }
-        else if (i < 2 * W) { k = 1; hh = H - 1; ww = i - W; }
-        else if (i < 2 * W + H) { k = 2; hh = i - 2 * W; ww = 0; }
-        else { k = 3; hh = i - 2 * W - H; ww = W - 1; }
-        const uint4 t = *reinterpret_cast<const uint4*>(img + ((size_t)hh * W + ww) * C + cq * 8);
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll 4
+    for (int i = pl; i < n_pix; i += lanes) {
+        const uint4 t = *reinterpret_cast<const uint4*>(img + base + (size_t)i * pitch + cq * 8);
         const __half2* h2 = reinterpret_cast<const __half2*>(&t);
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-            if (k == kk) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[kk][j] += v[j];
-            }
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); a[2 * j] += f.x; a[2 * j + 1] += f.y; }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[k][j][threadIdx.x] = a[k][j];
-    if (threadIdx.x < C) {
-        float t = 0.f;
-        for (int i = 0; i < n_part; ++i) t += part[((size_t)b * n_part + i) * C + threadIdx.x];
-        cls[0][threadIdx.x] = t;
-    }
+    for (int j = 0; j < 8; ++j) red[k][tk][j] = a[j];
     __syncthreads();
-    for (int o = threadIdx.x; o < 4 * C; o += 256) {
-        const int k = o / C, c = o % C;
+    for (int o = threadIdx.x; o < 5 * C; o += 256) {
+        const int kk = o / C, c = o % C;
         float t = 0.f;
-        for (int l = 0; l < lanes; ++l) t += red[k][c & 7][l * c8 + (c >> 3)];
-        cls[1 + k][c] = t;
+        if (kk == 0) {
+            for (int l = 0; l < 256 / C; ++l) t += tot[l][c];
+        } else {
+            for (int l = 0; l < lanes; ++l) t += red[kk - 1][l * c8 + (c >> 3)][c & 7];
+        }
+        cls[kk][c] = t;
     }
     __syncthreads();
     const float inv = 1.f / (float)(H * W);
@@ -454,7 +459,7 @@ int launch_se_apply(const SEW& se, const T* y, const T* res, const float* sums, 
 
 int launch_se_window(const __half* y, int B, int H, int W, int C, const float* part, int n_part, __half* win,
                      cudaStream_t s) {
-    if (C % 8 || C > 256 || 256 % (C / 8)) return -1;
+    if (C % 32 || C > 256 || 256 % C || 64 % (C / 8)) return -1;
     se_window_kernel<<<B, 256, 0, s>>>(y, H, W, C, part, n_part, win);
     return ok() ? 1 : -1;
 }
