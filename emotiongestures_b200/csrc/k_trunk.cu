@@ -39,28 +39,22 @@ template <> struct Vec4<__half> {
 };
 
 // ------------------------------------------------------------------------------------------
-// K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  grid (row strips, B).  The strip's input rows
-// (+1 halo row each side, zero padded) are staged in shared memory; a thread owns 8 output
-// channels whose 72 weights + bias / BN affine live in registers for the whole strip, so the
-// inner loop is 9 LDS + 72 FMA per 16-byte (8 x fp16) store.  Bandwidth-bound by construction:
-// 4*H*W bytes in, 2*32*H*W bytes out per clip, stores fully coalesced (a warp writes 512
-// contiguous bytes).
+// K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  Persistent CTAs walk (clip, 32-row strip) items.  A thread
+// owns 8 output channels whose 72 weights + bias / BN affine stay in registers for the whole kernel; the strip's
+// input rows (+1 halo row each side, zero padded) are staged in one of two shared-memory buffers, and the next
+// item's rows are already in flight (cp.async, zero fill for the padding) while the current strip is computed.  Inner loop: 9 LDS + 72 FMA
+// per 16-byte (8 x fp16) store; 4*H*W bytes in, 2*32*H*W bytes out per clip, a warp writes 512 contiguous bytes.
 // ------------------------------------------------------------------------------------------
-constexpr int kStemRows = 8;
+constexpr int kStemRows = 32;
 
 template <class T>
-__global__ void __launch_bounds__(256)
-stem_kernel(const float* __restrict__ spec, int H, int W, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2)
+stem_kernel(const float* __restrict__ spec, int H, int W, int strips, int n_items, const float* __restrict__ w,
             const float* __restrict__ bias, const float* __restrict__ scale,
             const float* __restrict__ shift, T* __restrict__ out) {
-    extern __shared__ float s_in[];                       // [(kStemRows + 2)][W + 2]
+    extern __shared__ float s_in[];                       // [2][(kStemRows + 2)][W + 2]
     const int PW = W + 2;
-    const int b = blockIdx.y, y0 = blockIdx.x * kStemRows;
-    const float* img = spec + (size_t)b * H * W;
-    for (int i = threadIdx.x; i < (kStemRows + 2) * PW; i += blockDim.x) {
-        const int yy = y0 + i / PW - 1, xx = i % PW - 1;
-        s_in[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[yy * W + xx] : 0.f;
-    }
+    const int n_stage = (kStemRows + 2) * PW;
     const int cg = threadIdx.x & 3;                        // channels [8*cg, 8*cg + 8)
     float wr[8][9], br[8], sr[8], tr[8];
 #pragma unroll
@@ -70,35 +64,58 @@ stem_kernel(const float* __restrict__ spec, int H, int W, const float* __restric
         for (int k = 0; k < 9; ++k) wr[j][k] = w[c * 9 + k];
         br[j] = bias[c]; sr[j] = scale[c]; tr[j] = shift[c];
     }
-    // pin the 96 parameters in registers: without this the compiler re-reads them from global memory inside the
-    // pixel loop (one LDG per FMA) instead of keeping them live
+    // pin the 96 parameters in registers (otherwise the compiler re-reads them from global memory inside the loop)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) asm volatile("" : "+f"(wr[j][k]));
         asm volatile("" : "+f"(br[j]), "+f"(sr[j]), "+f"(tr[j]));
     }
-    __syncthreads();
-    const int rows = min(kStemRows, H - y0);
-    for (int pix = threadIdx.x >> 2; pix < rows * W; pix += blockDim.x >> 2) {
-        const int ly = pix / W, x = pix - ly * W;
-        float tap[9];
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) tap[dy * 3 + dx] = s_in[(ly + dy) * PW + x + dx];
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float acc = br[j];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) acc = fmaf(wr[j][k], tap[k], acc);
-            v[j] = fmaxf(acc, 0.f) * sr[j] + tr[j];
+    // stage the padded strip of `item` into buffer sb with 4-byte cp.async copies (src-size 0 = zero fill for the padding)
+    auto stage = [&](int item, float* sb) {
+        const int b = item / strips, y0 = (item - b * strips) * kStemRows;
+        for (int i = threadIdx.x; i < n_stage; i += 256) {
+            const int yy = y0 + i / PW - 1, xx = i % PW - 1;
+            const bool inb = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const float* src = inb ? spec + ((size_t)b * H + yy) * W + xx : spec;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sb + i)),
+                         "l"(src), "r"(inb ? 4 : 0) : "memory");
         }
-        T* o = out + (((size_t)b * H + y0 + ly) * W + x) * 32 + cg * 8;
-        const float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
-        Vec4<T>::store(o, lo);
-        Vec4<T>::store(o + 4, hi);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int item = blockIdx.x;
+    if (item < n_items) stage(item, s_in);
+    int buf = 0;
+    for (; item < n_items; item += gridDim.x, buf ^= 1) {
+        float* sb = s_in + buf * n_stage;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // one barrier per item: the other buffer is two items old
+        if (item + (int)gridDim.x < n_items) stage(item + gridDim.x, s_in + (buf ^ 1) * n_stage);
+        const int b = item / strips, y0 = (item - b * strips) * kStemRows;
+        const int rows = min(kStemRows, H - y0);
+        int ly = 0, x = threadIdx.x >> 2;
+        while (x >= W) { x -= W; ++ly; }
+        for (; ly < rows;) {
+            float tap[9];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) tap[dy * 3 + dx] = sb[(ly + dy) * PW + x + dx];
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float acc = br[j];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc = fmaf(wr[j][k], tap[k], acc);
+                v[j] = fmaxf(acc, 0.f) * sr[j] + tr[j];
+            }
+            T* o = out + (((size_t)b * H + y0 + ly) * W + x) * 32 + cg * 8;
+            const float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
+            Vec4<T>::store(o, lo);
+            Vec4<T>::store(o + 4, hi);
+            x += 64;
+            while (x >= W) { x -= W; ++ly; }
+        }
     }
 }
 
@@ -419,9 +436,19 @@ inline bool ok() { return cudaGetLastError() == cudaSuccess; }
 
 template <class T>
 int launch_stem(const ConvW& c, const float* spec, int B, int H, int W, T* out, cudaStream_t s) {
-    dim3 grid((H + kStemRows - 1) / kStemRows, B);
-    const size_t smem = sizeof(float) * (kStemRows + 2) * (W + 2);
-    stem_kernel<T><<<grid, 256, smem, s>>>(spec, H, W, c.w32, c.bias, c.scale, c.shift, out);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    }
+    const int strips = (H + kStemRows - 1) / kStemRows;
+    const long n_items = (long)B * strips;
+    if (n_items > 0x7fffffffL) return -1;
+    const int n_stage = (kStemRows + 2) * (W + 2);
+    const size_t smem = sizeof(float) * 2 * n_stage;
+    if (smem > 48 * 1024) return -1;
+    const int grid = (int)std::min<long>(n_items, 2L * sms);
+    stem_kernel<T><<<grid, 256, smem, s>>>(spec, H, W, strips, (int)n_items, c.w32, c.bias, c.scale, c.shift, out);
     return ok() ? 1 : -1;
 }
 
