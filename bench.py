@@ -37,7 +37,9 @@ STAGE_WORK = {                        # (bound, work per clip): bytes for hbm, f
     "S1_frontend": ("hbm", 180_908.0),
     "S2_stem": ("hbm", 609_280.0),
     "S3_trunk_conv": ("tensor", 4.247e9),
-    "S4_se": ("hbm", 11.25e6),
+    # S4 (SE gate * y + residual + ReLU) is fused into conv2's epilogue; what is left under this tag are the three
+    # small launches per block that compute the gate ahead of conv2, so SURVEY.md §8(d) has S3+S4 reported jointly
+    # against the tensor roofline (see "S3+S4_trunk" below) and S4 alone carries no roofline of its own
     "S5_proj_gemm": ("tensor", 92e6),
     "S6_enc_dec": ("tensor", 442e6),
 }
@@ -50,6 +52,16 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"],
                 "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+def conv_traffic_per_launch(B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per trunk-convolution launch, from the committed ncu pass over one
+    step (profiles/r1_conv_dram.json, captured at `clips` clips and scaled linearly: every conv streams its maps once)."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_dram.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_per_launch"] * B / d["clips"]
 
 
 class ClockSampler:
@@ -269,11 +281,17 @@ def run_own_arm(args):
                     ent.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["tf_sustained"])
             per_stage[nm] = ent
         s3 = per_stage.get("S3_trunk_conv", {})
+        s4 = per_stage.get("S4_se", {})
+        if s3 and s4:
+            ms34 = s3["ms_per_step"] + s4["ms_per_step"]
+            ach = S3_FLOP_PER_CLIP * B / (ms34 * 1e-3) / 1e12
+            per_stage["S3+S4_trunk"] = {"ms_per_step": ms34, "launches_per_step": s3["launches_per_step"] + s4["launches_per_step"],
+                                        "bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
         n_conv = max(1.0, s3.get("launches_per_step", 1.0))
         roofline = {
             "bound": "tensor", "kernel": "trunk 3x3 convolutions (S3, %d launches per step)" % n_conv,
             "achieved": s3.get("achieved"), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": s3.get("frac"), "traffic": None,
+            "frac": s3.get("frac"), "traffic": conv_traffic_per_launch(B),
             "peak_source": peaks["src"] + " (sustained bf16/fp16 dense, kernel timed inside a long step)",
             "flop_per_launch": S3_FLOP_PER_CLIP * B / n_conv,
             "ms_per_launch": s3.get("ms_per_step", 0.0) / n_conv,
@@ -313,7 +331,7 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=32)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=512)
+    ap.add_argument("--e2e-chunk", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":
