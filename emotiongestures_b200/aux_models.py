@@ -197,6 +197,63 @@ class EmotionNet(_DeviceModule):
         return logits
 
 
+class _SkeletonPriorEncoder(nn.Module):
+    """skeleton_classifer/Models.py:87-121 (only fc1 -> Dropout -> fc2 is live)."""
+
+    def __init__(self, pose_dim, d_model):
+        super().__init__()
+        self.fc1 = nn.Linear(pose_dim, d_model)
+        self.fc2 = nn.Linear(d_model, d_model)
+
+
+class SkeletonClassifier(_DeviceModule):
+    """skeleton_classifer/Models.py:199-283 ``Transformer`` — the Emotion-ACC classifier the evaluation loop runs
+    on every generated batch (test_emotion_gesture_diversity_iterative.py:158,217).
+    Same constructor and state_dict layout; ``forward(prior_seq (B, n_position, pose_dim))`` returns
+    ``(logits (B, class_dim), mid_feature (B, n_position, d_model))`` like the reference.  The tcgen05 attention
+    kernel is specialised for d_k = d_v = 64, which is how the evaluation script builds the classifier."""
+
+    _family = "skel."
+
+    def __init__(self, class_dim=8, pose_dim=242, src_pad_idx=1, trg_pad_idx=1, d_word_vec=64, d_model=64,
+                 d_inner=512, n_layers=3, n_head=8, d_k=32, d_v=32, dropout=0.2, n_position=60):
+        super().__init__()
+        from .generator import _Encoder
+        assert d_model == d_word_vec
+        self.d_model = d_model
+        self.src_pad_idx, self.trg_pad_idx = src_pad_idx, trg_pad_idx
+        self.prior_seq_encoder = _SkeletonPriorEncoder(pose_dim, d_model)
+        self.post_projector = nn.Sequential(
+            nn.Linear(n_position * d_model, d_model * 4), nn.ReLU(True), nn.Linear(d_model * 4, d_model), nn.ReLU(True),
+            nn.Linear(d_model, 128), nn.ReLU(True), nn.Linear(128, 64), nn.ReLU(True), nn.Linear(64, class_dim))
+        self.dropout = nn.Dropout(p=dropout)
+        self.encoder = _Encoder(d_word_vec, n_layers, n_head, d_k, d_v, d_model, d_inner, n_position)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._dk = (d_k, d_v)
+
+    def forward(self, prior_seq):
+        if self._dk != (64, 64):
+            raise RuntimeError("SkeletonClassifier: the sm_100a attention kernel needs d_k = d_v = 64 "
+                               "(test_emotion_gesture_diversity_iterative.py:158 builds it that way)")
+        eng = self._engine()
+        x = eng._f32(prior_seq, "prior_seq")
+        if x.dim() != 3:
+            raise RuntimeError("prior_seq must be (B, n_frames, pose_dim)")
+        b, t, p = x.shape
+        n_class = self.post_projector[8].out_features
+        logits = torch.empty((b, n_class), device=eng.device)
+        mid = torch.empty((b, t, self.d_model), device=eng.device)
+        if b == 0:
+            return logits, mid
+        ws = torch.empty(int(eng.lib.egx_skeleton_workspace(eng._h, b)), dtype=torch.uint8, device=eng.device)
+        with torch.cuda.device(eng.device):
+            eng._check(eng.lib.egx_skeleton_forward(eng._h, _ptr(x), b, t, p, _ptr(logits), _ptr(mid), _ptr(ws), ws.numel(),
+                                                    eng._stream()), "egx_skeleton_forward")
+        return logits, mid
+
+
 def _conv_norm_relu(cin, cout, downsample=False):
     k, s = (4, 2) if downsample else (3, 1)
     return nn.Sequential(nn.Conv1d(cin, cout, kernel_size=k, stride=s), nn.BatchNorm1d(cout), nn.LeakyReLU(0.2, True))

@@ -261,12 +261,21 @@ struct Plan {
     }
 };
 
+// fp32 scratch of the Prior_MemoryEncoder front (0 for the plain Prior_ConvEncoder): pred | enc | pred_enc | S
+size_t mem_floats(const egx_handle* h, int B) {
+    const MemPriorW& m = h->w.mem;
+    if (!m.on) return 0;
+    const size_t P = h->cfg.pose_dim;
+    return (size_t)B * (m.n_pred * P + 2 * P + m.chunk) + P * m.chunk;
+}
+
 template <class T>
 struct Slots {
     T *act[3], *down;
     float* se_sums;
     float *fcin, *t0, *spec_feat, *pconv, *prior_feat, *h0, *h1, *h2, *fus_in, *x_a, *x_b, *pre;
     float *qkv, *attn_o, *hid, *enc_out, *dec_out, *post0, *post1, *post2;
+    float* mem;
 };
 
 template <class T>
@@ -285,6 +294,7 @@ Slots<T> plan_slots(const egx_handle* h, int B, Plan& p) {
     s.t0 = p.take<float>(R * c.d_model);
     s.spec_feat = p.take<float>(R * c.d_model);
     s.pconv = p.take<float>(R * c.pose_dim);
+    s.mem = p.take<float>(mem_floats(h, B));
     s.prior_feat = p.take<float>(R * c.d_model);
     s.h0 = p.take<float>((size_t)B * c.d_model);
     s.h1 = p.take<float>((size_t)B * 256);
@@ -348,6 +358,34 @@ int linear(egx_handle* h, const LinearW& w, const float* A, int M, float* C, int
 }
 
 // Runs the trunk; returns the buffer holding the output of `upto` (0 stem, 1..3 layers).
+// Prior encoder up to the (B, F, P) map its Linear pair consumes: the conv pair alone (Prior_ConvEncoder), or
+// pred_conv + spatial / temporal memory + cat(x, pred) (Prior_MemoryEncoder, see k_memory.cu).  scratch: mem_floats().
+
+template <class T>
+int run_prior_front(egx_handle* h, const float* prior, int B, float* scratch, T* out, int ldo, cudaStream_t s) {
+    const Weights& w = h->w;
+    const egx_cfg& c = h->cfg;
+    const int p = c.prior_frames, F = c.frames, P = c.pose_dim;
+    if (!w.mem.on) {
+        LAUNCH(h, launch_prior_conv<T>(w, prior, B, p, F, P, out, ldo, s));
+        return 0;
+    }
+    const MemPriorW& m = w.mem;
+    float* pred = scratch;
+    float* enc = pred + (size_t)B * m.n_pred * P;
+    float* pred_enc = enc + (size_t)B * 2 * P;
+    float* S = pred_enc + (size_t)B * m.chunk;
+    LAUNCH(h, launch_prior_conv<float>(w, prior, B, p, m.n_pred, P, pred, P, s));
+    GemmEpi e;
+    e.bias = m.enc.b;
+    // both chunk encoders on x[:, p-chunk:, :].reshape(B, chunk*P): a strided view of the prior poses
+    LAUNCH(h, launch_gemm_f32(prior + (size_t)(p - m.chunk) * P, p * P, m.enc.w, B, 2 * P, m.chunk * P, enc, 2 * P, e, s));
+    LAUNCH(h, launch_mem_spatial(pred, B, m.n_pred, P, m.chunk, enc, m.tm_w, m.tm_b, pred_enc, s));
+    LAUNCH(h, launch_mem_batch_outer(enc, pred_enc, B, P, m.chunk, S, s));
+    LAUNCH(h, launch_mem_temporal<T>(prior, pred, B, p, m.n_pred, P, m.chunk, enc, S, out, ldo, s));
+    return 0;
+}
+
 template <class T>
 int run_trunk(egx_handle* h, const float* spec, int B, Slots<T>& sl, int upto, T** result, cudaStream_t s) {
     T *x = sl.act[0], *y = sl.act[1], *z = sl.act[2];
@@ -410,7 +448,7 @@ int forward_impl(egx_handle* h, const float* spec, const float* prior, const flo
     if (linear(h, w.a_fc1, sl.fcin, R, sl.t0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.a_fc2, sl.t0, R, sl.spec_feat, 0, nullptr, 0, s)) return 1;
     // --- prior encoder (Full_model/Models.py:199-212) ---
-    LAUNCH(h, launch_prior_conv<float>(w, prior, B, c.prior_frames, F, c.pose_dim, sl.pconv, c.pose_dim, s));
+    if (run_prior_front<float>(h, prior, B, sl.mem, sl.pconv, c.pose_dim, s)) return 1;
     if (linear(h, w.p_fc1, sl.pconv, R, sl.t0, 0, nullptr, 0, s)) return 1;
     if (linear(h, w.p_fc2, sl.t0, R, sl.prior_feat, 0, nullptr, 0, s)) return 1;
     // --- emotion / semantic projections, classifier head (Models.py:411-415) ---
@@ -524,7 +562,7 @@ struct TcSlots {
     float *se_mean, *se_gate;
     __half *fcin, *t16, *spec16, *pconv16, *prior16, *emo16, *fus16, *h0, *h1, *h2, *x16, *x1_16, *qkv16, *o16,
         *hid16, *enc16, *dec16, *post0, *post1, *post2;
-    float *spec_feat, *prior_feat, *x32a, *x32b, *pre, *enc_out, *dec_out;
+    float *spec_feat, *prior_feat, *x32a, *x32b, *pre, *enc_out, *dec_out, *mem;
     int P8;
 };
 
@@ -546,6 +584,7 @@ TcSlots plan_tc(const egx_handle* h, int B, Plan& p) {
     s.t16 = p.take<__half>(R * d);
     s.spec16 = p.take<__half>(R * d);
     s.pconv16 = p.take<__half>(R * s.P8);
+    s.mem = p.take<float>(mem_floats(h, B));
     s.prior16 = p.take<__half>(R * d);
     s.emo16 = p.take<__half>(R * d);
     s.fus16 = p.take<__half>(R * d);
@@ -689,7 +728,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
     }
     StageScope sc5(h, 5);
     if (linear_tc(h, w.a_fc, sl.fcin, HW3, R, sl.spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
-    LAUNCH(h, launch_prior_conv<__half>(w, prior, B, c.prior_frames, F, P, sl.pconv16, P8, s));
+    if (run_prior_front<__half>(h, prior, B, sl.mem, sl.pconv16, P8, s)) return 1;
     if (linear_tc(h, w.p_fc, sl.pconv16, P8, R, sl.prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.emo, sl.spec16, d, R, emo_feat, d, sl.emo16, d, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.sem, sl.spec16, d, R, sem_feat, d, nullptr, 0, 0, nullptr, 0, s)) return 1;
@@ -1089,6 +1128,69 @@ int pack_fgd_mlp(egx_handle* h) {
     return 0;
 }
 
+// (f)2: skeleton_classifer/Models.py:199-283 (Transformer), :87-121 (Prior_Encoder), :127-172 (Encoder)
+int pack_skeleton(egx_handle* h) {
+    BucketScope scope(h, "skel");
+    h->skel = SkeletonW();
+    SkeletonW& k = h->skel;
+    const HostTensor* fc1 = find(h, "skel.prior_seq_encoder.fc1.weight");
+    const HostTensor* pt = find(h, "skel.encoder.position_enc.pos_table");
+    const HostTensor* wq = find(h, "skel.encoder.layer_stack.0.slf_attn.w_qs.weight");
+    const HostTensor* w1 = find(h, "skel.encoder.layer_stack.0.pos_ffn.w_1.weight");
+    const HostTensor* last = find(h, "skel.post_projector.8.weight");
+    if (!fc1 || !pt || !wq || !w1 || !last || fc1->shape.size() != 2 || pt->shape.size() != 3 || wq->shape.size() != 2 ||
+        w1->shape.size() != 2 || last->shape.size() != 2)
+        EGX_FAIL(h, "skeleton classifier: missing prior_seq_encoder / encoder / post_projector weights");
+    k.d = (int)fc1->shape[0]; k.P = (int)fc1->shape[1];
+    k.T = (int)pt->shape[1];
+    k.d_inner = (int)w1->shape[0];
+    k.n_class = (int)last->shape[0];
+    if (wq->shape[0] % 64 || (int)pt->shape[2] != k.d || k.d % 8)
+        EGX_FAIL(h, "skeleton classifier: the attention kernel needs d_k = d_v = 64 (as the evaluation script builds it)");
+    k.n_head = (int)wq->shape[0] / 64;
+    while (find(h, "skel.encoder.layer_stack." + std::to_string(k.n_layers) + ".slf_attn.w_qs.weight")) ++k.n_layers;
+    if (!make_collapsed(h, {"skel.prior_seq_encoder.fc1", "skel.prior_seq_encoder.fc2"}, {k.P, k.d, k.d}, &k.prior)) return 1;
+    k.pos_table = upload(h, pt->v);
+    egx_cfg c{};
+    c.d_model = k.d; c.d_inner = k.d_inner; c.n_head = k.n_head; c.d_k = 64; c.d_v = 64;
+    k.attn.resize(k.n_layers); k.ffn.resize(k.n_layers);
+    for (int l = 0; l < k.n_layers; ++l) {
+        const std::string e = "skel.encoder.layer_stack." + std::to_string(l);
+        if (!make_mha(h, e + ".slf_attn", c, &k.attn[l]) || !make_ffn(h, e + ".pos_ffn", c, &k.ffn[l])) return 1;
+    }
+    const int dims[6] = {k.T * k.d, 4 * k.d, k.d, 128, 64, k.n_class};
+    for (int i = 0; i < 5; ++i)
+        if (!make_linear(h, "skel.post_projector." + std::to_string(2 * i), dims[i], dims[i + 1], true, &k.post[i])) return 1;
+    if (!scope.ok()) EGX_FAIL(h, "device allocation failed while packing the skeleton classifier");
+    k.ready = true;
+    return 0;
+}
+
+struct SkelSlots {
+    __half *a16, *x16, *x1_16, *qkv16, *o16, *hid16, *p16[4];
+    float *x32a, *x32b, *pre;
+    int P8;
+};
+
+SkelSlots plan_skeleton(const SkeletonW& k, int B, Plan& p) {
+    SkelSlots s;
+    const size_t R = (size_t)B * k.T;
+    const int hk = k.n_head * 64;
+    s.P8 = (k.P + 7) / 8 * 8;
+    s.a16 = p.take<__half>(R * s.P8);
+    s.x16 = p.take<__half>(R * k.d);
+    s.x1_16 = p.take<__half>(R * k.d);
+    s.qkv16 = p.take<__half>(R * 3 * hk);
+    s.o16 = p.take<__half>(R * hk);
+    s.hid16 = p.take<__half>(R * k.d_inner);
+    const int pd[4] = {4 * k.d, k.d, 128, 64};
+    for (int i = 0; i < 4; ++i) s.p16[i] = p.take<__half>((size_t)B * pd[i]);
+    s.x32a = p.take<float>(R * k.d);
+    s.x32b = p.take<float>(R * k.d);
+    s.pre = p.take<float>(R * k.d);
+    return s;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -1167,6 +1269,7 @@ int egx_finalize_weights(egx_handle* h) {
     if (h->staged.count("pose_enc.net.0.0.weight")) { if (pack_pose_enc(h, "pose_enc", "pose_enc.", true, &h->pose_enc)) return 1; ++packed; }
     if (h->staged.count("fgd_mlp.Encoder.0.weight")) { if (pack_fgd_mlp(h)) return 1; ++packed; }
     if (h->staged.count("emotion_net.emotion_encoder.conv1.weight")) { if (pack_emotion_net(h)) return 1; ++packed; }
+    if (h->staged.count("skel.prior_seq_encoder.fc1.weight")) { if (pack_skeleton(h)) return 1; ++packed; }
     if (!h->staged.count("audio_encoder.feat_extractor.conv1.weight")) {
         if (!packed) EGX_FAIL(h, "no known weight family staged");
         h->staged.clear();
@@ -1187,18 +1290,50 @@ int egx_finalize_weights(egx_handle* h) {
     const int d = c.d_model, F = c.frames, P = c.pose_dim, p = c.prior_frames;
     if (!make_linear(h, "audio_encoder.fc1", h->H[2] * h->W[2], d, true, &w.a_fc1)) return 1;
     if (!make_linear(h, "audio_encoder.fc2", d, d, true, &w.a_fc2)) return 1;
+    // Prior encoder: Prior_ConvEncoder (Full_model/Models.py:186-212) or, when the checkpoint carries them, the
+    // Prior_MemoryEncoder keys of Full_model/Models_memory.py:296-345 (same conv-ReLU-BN pair, p -> F-p frames)
+    const bool memory = find(h, "prior_seq_encoder.pred_conv.0.weight") != nullptr;
+    const std::string pe = "prior_seq_encoder.";
+    const std::string k_c1 = memory ? pe + "pred_conv.0" : pe + "conv1", k_b1 = memory ? pe + "pred_conv.2" : pe + "bn1";
+    const std::string k_c2 = memory ? pe + "pred_conv.3" : pe + "conv2", k_b2 = memory ? pe + "pred_conv.5" : pe + "bn2";
+    const std::string k_f1 = memory ? pe + "post_header.0" : pe + "fc1", k_f2 = memory ? pe + "post_header.2" : pe + "fc2";
+    const int Fc = memory ? F - p : F;       // frames the conv pair produces
     {
         const HostTensor *c1w, *c1b, *c2w, *c2b;
-        if (!need(h, "prior_seq_encoder.conv1.weight", {F, p, 3}, &c1w) || !need(h, "prior_seq_encoder.conv1.bias", {F}, &c1b) ||
-            !need(h, "prior_seq_encoder.conv2.weight", {F, F, 3}, &c2w) || !need(h, "prior_seq_encoder.conv2.bias", {F}, &c2b))
+        if (!need(h, k_c1 + ".weight", {Fc, p, 3}, &c1w) || !need(h, k_c1 + ".bias", {Fc}, &c1b) ||
+            !need(h, k_c2 + ".weight", {Fc, Fc, 3}, &c2w) || !need(h, k_c2 + ".bias", {Fc}, &c2b))
             return 1;
         std::vector<float> s1, t1, s2, t2;
-        if (!fold_bn(h, "prior_seq_encoder.bn1", F, s1, t1) || !fold_bn(h, "prior_seq_encoder.bn2", F, s2, t2)) return 1;
+        if (!fold_bn(h, k_b1, Fc, s1, t1) || !fold_bn(h, k_b2, Fc, s2, t2)) return 1;
         w.p_c1w = upload(h, c1w->v); w.p_c1b = upload(h, c1b->v); w.p_s1 = upload(h, s1); w.p_t1 = upload(h, t1);
         w.p_c2w = upload(h, c2w->v); w.p_c2b = upload(h, c2b->v); w.p_s2 = upload(h, s2); w.p_t2 = upload(h, t2);
     }
-    if (!make_linear(h, "prior_seq_encoder.fc1", P, d, true, &w.p_fc1)) return 1;
-    if (!make_linear(h, "prior_seq_encoder.fc2", d, d, true, &w.p_fc2)) return 1;
+    if (memory) {
+        const HostTensor* sw = find(h, pe + "spatial_memory.spatial_chunk_encoder.0.weight");
+        if (!sw || sw->shape.size() != 2 || sw->shape[0] != P || sw->shape[1] % P)
+            EGX_FAIL(h, "prior_seq_encoder.spatial_memory.spatial_chunk_encoder.0.weight: expected (P, chunk*P)");
+        MemPriorW& m = w.mem;
+        m.chunk = (int)(sw->shape[1] / P);
+        m.n_pred = Fc;
+        if (m.chunk < 1 || m.chunk > p || m.chunk > Fc) EGX_FAIL(h, "memory chunk must not exceed prior_frames or frames - prior_frames");
+        const int CP = m.chunk * P;
+        Affine sp, tm, te;
+        if (!linear_chain(h, pe + "spatial_memory.spatial_chunk_encoder", {0, 2}, {CP, P, P}, &sp) ||
+            !linear_chain(h, pe + "temporal_memory.temporal_chunk_encoder", {0, 2}, {CP, P, P}, &tm) ||
+            !linear_chain(h, pe + "temporal_memory.temporal_memory_encoder", {0, 2}, {CP, m.chunk, m.chunk}, &te))
+            return 1;
+        std::vector<double> W2 = sp.W, b2 = sp.b;
+        W2.insert(W2.end(), tm.W.begin(), tm.W.end());
+        b2.insert(b2.end(), tm.b.begin(), tm.b.end());
+        m.enc.in = CP; m.enc.out = 2 * P;
+        m.enc.w = upload(h, to_f32(W2));
+        m.enc.b = upload(h, to_f32(b2));
+        m.tm_w = upload(h, to_f32(te.W));
+        m.tm_b = upload(h, to_f32(te.b));
+        m.on = true;
+    }
+    if (!make_linear(h, k_f1, P, d, true, &w.p_fc1)) return 1;
+    if (!make_linear(h, k_f2, d, d, true, &w.p_fc2)) return 1;
     if (!make_linear(h, "emotion_proj.0", d, d, true, &w.emo0) || !make_linear(h, "emotion_proj.2", d, d, true, &w.emo2) ||
         !make_linear(h, "semantic_proj.0", d, d, true, &w.sem0) || !make_linear(h, "semantic_proj.2", d, d, true, &w.sem2) ||
         !make_linear(h, "fusion_proj.0", d, d, true, &w.fus0) || !make_linear(h, "fusion_proj.2", d, d, true, &w.fus2))
@@ -1210,7 +1345,7 @@ int egx_finalize_weights(egx_handle* h) {
     for (int i = 0; i < 4; ++i)
         if (!make_linear(h, "post_projector." + std::to_string(2 * i), post_in[i], post_out[i], true, &w.post[i])) return 1;
     if (!make_collapsed(h, {"audio_encoder.fc1", "audio_encoder.fc2"}, {h->H[2] * h->W[2], d, d}, &w.a_fc) ||
-        !make_collapsed(h, {"prior_seq_encoder.fc1", "prior_seq_encoder.fc2"}, {P, d, d}, &w.p_fc) ||
+        !make_collapsed(h, {k_f1, k_f2}, {P, d, d}, &w.p_fc) ||
         !make_collapsed(h, {"emotion_proj.0", "emotion_proj.2"}, {d, d, d}, &w.emo) ||
         !make_collapsed(h, {"semantic_proj.0", "semantic_proj.2"}, {d, d, d}, &w.sem) ||
         !make_collapsed(h, {"post_projector.0", "post_projector.2", "post_projector.4", "post_projector.6"}, {d, 4 * d, d, P, P},
@@ -1490,6 +1625,67 @@ int egx_emotion_net_forward(egx_handle* h, const float* spec, int n_clips, int n
         if (linear_tc(h, l, a, l.in, n_clips, i == 5 ? logits : nullptr, 8, i < 5 ? sl.fc[i] : nullptr, l.out, i < 5, nullptr, 0, s))
             return 1;
         if (i < 5) a = sl.fc[i];
+    }
+    return 0;
+}
+
+size_t egx_skeleton_workspace(const egx_handle* h, int n_clips) {
+    if (!h || !h->skel.ready || n_clips <= 0) return 0;
+    Plan p;
+    plan_skeleton(h->skel, n_clips, p);
+    return p.off + 256;
+}
+
+int egx_skeleton_dims(const egx_handle* h, int* n_frames, int* pose_dim, int* d_model, int* n_class) {
+    if (!h || !h->skel.ready) return 1;
+    if (n_frames) *n_frames = h->skel.T;
+    if (pose_dim) *pose_dim = h->skel.P;
+    if (d_model) *d_model = h->skel.d;
+    if (n_class) *n_class = h->skel.n_class;
+    return 0;
+}
+
+int egx_skeleton_forward(egx_handle* h, const float* poses, int n_clips, int n_frames, int pose_dim, float* logits,
+                         float* mid_feature, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return 1;
+    const SkeletonW& k = h->skel;
+    if (!k.ready) EGX_FAIL(h, "skeleton classifier weights not loaded");
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || !poses || !logits || !workspace) EGX_FAIL(h, "null pointer argument");
+    if (n_frames != k.T || pose_dim != k.P)
+        EGX_FAIL(h, "poses (n," + std::to_string(n_frames) + "," + std::to_string(pose_dim) + ") do not match the classifier's (" +
+                        std::to_string(k.T) + "," + std::to_string(k.P) + ") input (post_projector flattens n_position frames)");
+    cudaStream_t s = (cudaStream_t)stream;
+    Plan p;
+    p.base = static_cast<char*>(workspace);
+    SkelSlots sl = plan_skeleton(k, n_clips, p);
+    if (p.off > workspace_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
+    const int B = n_clips, R = B * k.T, d = k.d, hk = k.n_head * 64;
+    StageScope sc(h, 6);
+    LAUNCH(h, launch_cvt_pad_f16(poses, R, k.P, k.P, sl.a16, sl.P8, s));
+    // Prior_Encoder, then PositionalEncoding.forward: x + pos_table[:, :T] (skeleton_classifer/Models.py:49-50,109-113)
+    if (linear_tc(h, k.prior, sl.a16, sl.P8, R, sl.x32a, d, sl.x16, d, 0, k.pos_table, k.T, s)) return 1;
+    float *x32 = sl.x32a, *y32 = sl.x32b;
+    for (int l = 0; l < k.n_layers; ++l) {
+        const MHAW& a = k.attn[l];
+        const FFNW& f = k.ffn[l];
+        if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
+        LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, k.T, k.n_head, sl.o16, hk, s));
+        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, x32, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, k.d_inner, 1, nullptr, 0, s)) return 1;
+        if (linear_tc(h, f.w2, sl.hid16, k.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, x32, sl.x16, s));
+    }
+    if (mid_feature) EGX_CHECK_CUDA(h, cudaMemcpyAsync(mid_feature, x32, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // enc_output.reshape(B, -1) -> post_projector (:277-281): rows of x16 are already (clip, frame)-major
+    const __half* a = sl.x16;
+    int lda = k.T * d;
+    for (int i = 0; i < 5; ++i) {
+        const LinearW& l = k.post[i];
+        if (linear_tc(h, l, a, lda, B, i == 4 ? logits : nullptr, l.out, i < 4 ? sl.p16[i] : nullptr, l.out, i < 4, nullptr, 0, s))
+            return 1;
+        if (i < 4) { a = sl.p16[i]; lda = l.out; }
     }
     return 0;
 }

@@ -62,6 +62,14 @@ struct BlockW {
 struct MHAW { LinearW q, k, v, kv, qkv, fc; LNW ln; };
 struct FFNW { LinearW w1, w2; LNW ln; };
 
+// (f)1  Full_model/Models_memory.py Prior_MemoryEncoder (the prior encoder of the checkpointed generator)
+struct MemPriorW {
+    bool on = false;
+    int chunk = 0, n_pred = 0;
+    LinearW enc;                      // [2P][chunk*P]: spatial_chunk_encoder | temporal_chunk_encoder, each collapsed
+    float *tm_w = nullptr, *tm_b = nullptr;   // temporal_memory_encoder collapsed: [chunk][chunk*P], [chunk]
+};
+
 struct Weights {
     ConvW stem;                       // 1->32, bias, relu_first, bn
     std::vector<BlockW> blocks;       // 13 SEBasicBlocks
@@ -70,7 +78,8 @@ struct Weights {
     // prior encoder
     float *p_c1w = nullptr, *p_c1b = nullptr, *p_s1 = nullptr, *p_t1 = nullptr;
     float *p_c2w = nullptr, *p_c2b = nullptr, *p_s2 = nullptr, *p_t2 = nullptr;
-    LinearW p_fc1, p_fc2;
+    LinearW p_fc1, p_fc2;             // Prior_ConvEncoder fc1 / fc2, or Prior_MemoryEncoder post_header.0 / .2
+    MemPriorW mem;
     LinearW emo0, emo2, sem0, sem2, fus0, fus2;
     LinearW hdr[4];
     LinearW post[4];
@@ -129,6 +138,19 @@ struct EmotionNetW {
     bool ready = false;
 };
 
+// (f)2  skeleton_classifer/Models.py Transformer: the Emotion-ACC classifier run on every generated batch
+// (test_emotion_gesture_diversity_iterative.py:158,217): Linear chain -> + sinusoid rows -> n_layers EncoderLayers
+// -> flatten -> Linear+ReLU x4 -> Linear.  fp16 tensor-core arm only, d_k = d_v = 64.
+struct SkeletonW {
+    int T = 0, P = 0, d = 0, d_inner = 0, n_layers = 0, n_head = 0, n_class = 0;
+    LinearW prior;                    // prior_seq_encoder.fc1 -> Dropout -> fc2 collapsed
+    float* pos_table = nullptr;       // [T][d]
+    std::vector<MHAW> attn;
+    std::vector<FFNW> ffn;
+    LinearW post[5];
+    bool ready = false;
+};
+
 // Log-mel tables (built in float64 on the host, stored as float32)
 struct LogmelTables {
     float* window = nullptr;      // [1024] periodic Hann
@@ -157,6 +179,7 @@ struct egx_handle {
     egx::PoseEncW motion_ae, pose_enc;
     egx::RowMlpW fgd_mlp;
     egx::EmotionNetW emo;
+    egx::SkeletonW skel;
     int64_t launches = 0;
     // per-launch CUDA-event profiling (egx_profile_enable / egx_profile_read)
     bool profiling = false;
@@ -274,6 +297,14 @@ int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, 
 
 int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
                           cudaStream_t s);
+
+// ---- k_memory.cu (Prior_MemoryEncoder between pred_conv and post_header) ----
+int launch_mem_spatial(float* pred, int B, int n_pred, int P, int C, const float* enc, const float* tm_w, const float* tm_b,
+                       float* pred_enc, cudaStream_t s);
+int launch_mem_batch_outer(const float* enc, const float* pred_enc, int B, int P, int C, float* S, cudaStream_t s);
+template <class T>
+int launch_mem_temporal(const float* prior, const float* pred, int B, int p, int n_pred, int P, int C, const float* enc,
+                        const float* S, T* out, int ldo, cudaStream_t s);
 
 // ---- k_aux.cu ----
 int launch_cvae_mlp(const CvaeW& w, const float* x, const float* y, const float* noise, int noise_is_z, int64_t n,

@@ -177,6 +177,45 @@ class _PriorEncoder(nn.Module):
         self.fc2 = nn.Linear(d_model, d_model)
 
 
+class _ChunkEncoder(nn.Sequential):
+    """Linear -> Dropout(0.2) -> Linear, the Sequential index layout of the memory nets."""
+
+    def __init__(self, d_in, d_out):
+        super().__init__(nn.Linear(d_in, d_out), nn.Dropout(0.2), nn.Linear(d_out, d_out))
+
+
+class _SpatialMemory(nn.Module):
+    """Full_model/Models_memory.py:215-231 (SP_Memory_Net_v1 parameters)."""
+
+    def __init__(self, chunk, pose_dim):
+        super().__init__()
+        self.spatial_chunk_encoder = _ChunkEncoder(chunk * pose_dim, pose_dim)
+
+
+class _TemporalMemory(nn.Module):
+    """Full_model/Models_memory.py:263-281 (TM_Memory_Net parameters)."""
+
+    def __init__(self, chunk, pose_dim):
+        super().__init__()
+        self.temporal_chunk_encoder = _ChunkEncoder(chunk * pose_dim, pose_dim)
+        self.temporal_memory_encoder = _ChunkEncoder(chunk * pose_dim, chunk)
+
+
+class _PriorMemoryEncoder(nn.Module):
+    """Full_model/Models_memory.py:296-345 (parameters only; the arithmetic runs in libegx, k_memory.cu)."""
+
+    def __init__(self, args, prior_frames, frames, pose_dim, d_model):
+        super().__init__()
+        self.post_header = nn.Sequential(nn.Linear(pose_dim, d_model), nn.Dropout(0.2), nn.Linear(d_model, d_model))
+        self.pred_length = frames - prior_frames
+        n = self.pred_length
+        self.pred_conv = nn.Sequential(
+            nn.Conv1d(prior_frames, n, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=True), nn.BatchNorm1d(n),
+            nn.Conv1d(n, n, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=True), nn.BatchNorm1d(n))
+        self.spatial_memory = _SpatialMemory(args.chunk, pose_dim)
+        self.temporal_memory = _TemporalMemory(args.chunk, pose_dim)
+
+
 class _MHA(nn.Module):
     """Full_model/SubLayers.py:12-27 (no biases, LayerNorm eps 1e-6)."""
 
@@ -347,6 +386,42 @@ class Transformer(nn.Module):
         eng = self.engine(getattr(self, "precision", "tc"))
         spec = eng.logmel(audio, LOGMEL_LOG_IN if mode is None else mode, preemph)
         return self.forward(spec, text, prior_seq, sampled_emotion_feature)
+
+
+class MemoryTransformer(Transformer):
+    """Drop-in for Full_model.Models_memory.Transformer (:428-560), the generator the evaluation script really loads
+    (test_emotion_gesture_diversity_iterative.py:25,135): identical to ``Transformer`` except that the prior-pose
+    encoder is ``Prior_MemoryEncoder`` (``args.chunk`` frames of spatial / temporal memory).  Its temporal memory
+    sums over the batch of the call (Models_memory.py:287-288), so — exactly as in the reference — a clip's poses
+    depend on which other clips share its batch / DataParallel replica."""
+
+    def __init__(self, args, lang_model, *a, **k):
+        super().__init__(args, lang_model, *a, **k)
+        c = self.cfg
+        self.prior_seq_encoder = _PriorMemoryEncoder(args, c.prior_frames, c.frames, c.pose_dim, c.d_model)
+        for p in self.prior_seq_encoder.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    @classmethod
+    def from_config(cls, cfg: GeneratorConfig, chunk: int = 4, dropout=0.1):
+        class _Args:
+            freeze_wordembed = False
+            hidden_size = cfg.tcn_hidden
+            n_layers = cfg.tcn_layers
+            wordembed_dim = cfg.wordembed_dim
+            dropout_prob = 0.1
+
+        class _Lang:
+            n_words = cfg.n_words
+            word_embedding_weights = None
+
+        _Args.chunk = chunk
+        return cls(_Args(), _Lang(), frames=cfg.frames, pose_dim=cfg.pose_dim,
+                   prior_frames=cfg.prior_frames, d_word_vec=cfg.d_model, d_model=cfg.d_model,
+                   d_inner=cfg.d_inner, n_layers=cfg.n_layers, n_head=cfg.n_head, d_k=cfg.d_k,
+                   d_v=cfg.d_v, dropout=dropout, n_position=cfg.n_position, spec_w=cfg.spec_w,
+                   n_audio=cfg.n_audio)
 
 
 def randomize_norm_stats_(module: nn.Module, seed: int = 1) -> None:

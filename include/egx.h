@@ -154,6 +154,16 @@ EGX_API size_t egx_emotion_net_workspace(const egx_handle* h, int n_clips, int n
 EGX_API int  egx_emotion_net_forward(egx_handle* h, const float* spec, int n_clips, int n_mels, int n_cols,
                              float* logits, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces: skeleton_classifer/Models.py Transformer.forward (:264-283), the Emotion-ACC classifier the evaluation
+ * loop runs on every generated batch (test_emotion_gesture_diversity_iterative.py:158,217); weights under the
+ * "skel." prefix, geometry read from their shapes (d_k = d_v = 64 as the evaluation script builds it).
+ * poses (n, n_frames, pose_dim) f32 with n_frames == n_position -> logits (n, class_dim) f32 and, when mid_feature is
+ * not NULL, the encoder output (n, n_frames, d_model) f32 (the second value the reference returns). */
+EGX_API size_t egx_skeleton_workspace(const egx_handle* h, int n_clips);
+EGX_API int  egx_skeleton_forward(egx_handle* h, const float* poses, int n_clips, int n_frames, int pose_dim,
+                          float* logits, float* mid_feature, void* workspace, size_t workspace_bytes, void* stream);
+EGX_API int  egx_skeleton_dims(const egx_handle* h, int* n_frames, int* pose_dim, int* d_model, int* n_class);
+
 /* Parity probe of the tcgen05 Linear kernel alone: out = [relu](A W^T + bias) + addend, A (M,K), W (N,K),
  * out (M,N) f32; operands are rounded to fp16 inside.  Synchronises the stream (test-only). */
 EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias,

@@ -86,5 +86,27 @@ def emotion_net(sd, mfcc, taps=None):
     return _lin(sd, "last_fc", x)
 
 
+def skeleton_classifier(sd, poses, n_head=8, d_k=64):
+    """skeleton_classifer/Models.py:264-283: Prior_Encoder (:109-113) -> + pos_table[:, :T] (:49-50) ->
+    EncoderLayers (Layers.py / SubLayers.py, byte-identical copies of the generator's) -> flatten -> post_projector."""
+    from oracle import generator as og
+    x = _lin(sd, "prior_seq_encoder.fc2", _lin(sd, "prior_seq_encoder.fc1", poses))
+    x = x + sd["encoder.position_enc.pos_table"][:, :x.shape[1]].to(x.dtype)
+    n_layers = 0
+    while f"encoder.layer_stack.{n_layers}.slf_attn.w_qs.weight" in sd:
+        n_layers += 1
+    for l in range(n_layers):
+        pre = f"encoder.layer_stack.{l}"
+        x, _ = og.mha(sd, pre + ".slf_attn", x, x, n_head, d_k, d_k)
+        x = og.ffn(sd, pre + ".pos_ffn", x)
+    mid = x
+    h = x.reshape(x.shape[0], -1)
+    for i in range(5):
+        h = _lin(sd, f"post_projector.{2 * i}", h)
+        if i < 4:
+            h = torch.relu(h)
+    return h, mid
+
+
 def cast(sd, dtype):
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -92,6 +92,35 @@ def prior_encoder(sd, prior):
     return _linear(sd, pre + ".fc2", _linear(sd, pre + ".fc1", x))
 
 
+def prior_memory_encoder(sd, prior):
+    """Full_model/Models_memory.py:335-345 with SP_Memory_Net_v1.forward (:233-249) and TM_Memory_Net.forward
+    (:282-293).  The reference's B x chunk Python loop of torch.mm is one batched dot product here."""
+    pre = "prior_seq_encoder."
+    b, p, P = prior.shape
+    chunk = sd[pre + "spatial_memory.spatial_chunk_encoder.0.weight"].shape[1] // P
+
+    def chain(name, x):
+        return _linear(sd, pre + name + ".2", _linear(sd, pre + name + ".0", x))
+
+    x = F.conv1d(prior, sd[pre + "pred_conv.0.weight"], sd[pre + "pred_conv.0.bias"], padding=1)
+    x = _bn(sd, pre + "pred_conv.2", F.relu(x))
+    x = F.conv1d(x, sd[pre + "pred_conv.3.weight"], sd[pre + "pred_conv.3.bias"], padding=1)
+    pred = _bn(sd, pre + "pred_conv.5", F.relu(x))
+    tail = prior[:, p - chunk:, :].reshape(b, -1)
+    # spatial memory
+    mem = chain("spatial_memory.spatial_chunk_encoder", tail)                       # (B, P)
+    head = pred[:, :chunk, :]
+    s = torch.sigmoid(torch.einsum("bp,bcp->bc", mem, head)).unsqueeze(2)
+    head = s * head + (1 - s) * mem.unsqueeze(1)
+    # temporal memory (note the sum over the batch in mem^T e)
+    mem_t = chain("temporal_memory.temporal_chunk_encoder", tail)                   # (B, P)
+    e = chain("temporal_memory.temporal_memory_encoder", head.reshape(b, -1))       # (B, chunk)
+    soft = torch.softmax(mem_t @ (mem_t.t() @ e), dim=1)
+    head = head + head * soft.unsqueeze(2)
+    out = torch.cat((prior, head, pred[:, chunk:, :]), 1)
+    return chain("post_header", out)
+
+
 def mha(sd, pre, q_in, kv_in, n_head, d_k, d_v):
     """Full_model/SubLayers.py:30-59 + Full_model/Modules.py:13-23 (mask None, eval)."""
     b, lq, _ = q_in.shape
@@ -120,7 +149,8 @@ def generator_forward(sd, cfg, spec, prior, sampled_emotion=None, taps=None):
     Returns (poses, emotion_feature, semantic_feature, emotion_logits).
     """
     x = audio_encoder(sd, spec.unsqueeze(1), taps)
-    p = prior_encoder(sd, prior)
+    memory = "prior_seq_encoder.pred_conv.0.weight" in sd           # Models_memory.Transformer checkpoints
+    p = prior_memory_encoder(sd, prior) if memory else prior_encoder(sd, prior)
     if taps is not None:
         taps["spectrum_feature"] = x
         taps["prior_feature"] = p

@@ -21,16 +21,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from emotiongestures_b200 import BEAT, TED, Transformer  # noqa: E402
+from emotiongestures_b200.generator import MemoryTransformer  # noqa: E402
 from oracle import generator as og  # noqa: E402
 from oracle import synth  # noqa: E402
 
 REF = "/root/reference"
 
 
-def load_reference(cfg):
+def load_reference(cfg, chunk=0):
+    """Full_model.Models.Transformer, or (chunk > 0) Full_model.Models_memory.Transformer with args.chunk = chunk."""
     sys.path.insert(0, REF)
     sys.modules.setdefault("torch_dct", types.ModuleType("torch_dct"))
-    from Full_model.Models import Transformer as RefTransformer
+    if chunk:
+        from Full_model.Models_memory import Transformer as RefTransformer
+    else:
+        from Full_model.Models import Transformer as RefTransformer
 
     class Args:
         freeze_wordembed = False
@@ -38,6 +43,8 @@ def load_reference(cfg):
         n_layers = cfg.tcn_layers
         wordembed_dim = cfg.wordembed_dim
         dropout_prob = 0.1
+
+    Args.chunk = chunk
 
     class Lang:
         n_words = cfg.n_words
@@ -56,9 +63,9 @@ def load_reference(cfg):
     return g.eval()
 
 
-def run(cfg, name, n_clips, seed, with_emotion):
-    ref = load_reference(cfg)
-    mine = Transformer.from_config(cfg).eval()
+def run(cfg, name, n_clips, seed, with_emotion, chunk=0):
+    ref = load_reference(cfg, chunk)
+    mine = (MemoryTransformer.from_config(cfg, chunk) if chunk else Transformer.from_config(cfg)).eval()
     tmpl = mine.state_dict()
     ref_sd = ref.state_dict()
     assert list(tmpl.keys()) == list(ref_sd.keys()), "state_dict key layout differs from reference"
@@ -80,7 +87,9 @@ def run(cfg, name, n_clips, seed, with_emotion):
         hooks.append(m.register_forward_hook(
             lambda _m, _i, o, nm=nm: taps_ref.__setitem__(nm, (o[0] if isinstance(o, tuple) else o).detach().clone())))
     with torch.no_grad():
-        if with_emotion:
+        if with_emotion and chunk:
+            ref_out = ref(spec, text, prior, emo_in)          # Models_memory.py:521 takes the 4th argument itself
+        elif with_emotion:
             # Models.py has no 4th argument; apply Models_memory.py:551-555 by patching the sum
             # exactly as that file does: fusion = sampled + semantic.
             sys.modules.setdefault("torch_dct", types.ModuleType("torch_dct"))
@@ -147,3 +156,5 @@ if __name__ == "__main__":
     print("TED"); run(TED, "ted_b2", 2, 0, False)
     print("TED + emotion injection"); run(TED, "ted_b2_emotion", 2, 3, True)
     print("BEAT"); run(BEAT, "beat_b1", 1, 1, False)
+    # Models_memory.Transformer (Prior_MemoryEncoder); 3 clips so that the temporal memory's batch sum is exercised
+    print("TED, memory prior encoder, chunk 4"); run(TED, "tedmem_b3", 3, 5, True, chunk=4)

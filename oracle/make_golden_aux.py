@@ -153,7 +153,7 @@ def main():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if "--emotion-net" not in sys.argv:
+    if "--emotion-net" not in sys.argv and "--skeleton" not in sys.argv:
         main()
     for f in sorted(os.listdir(GOLD)):
         if f.startswith("aux_"):
@@ -187,5 +187,31 @@ def emotion_net_golden():
                         layer4_mean=taps_ref["layer4"].double().mean(dim=(2, 3)).numpy().astype(np.float32))
 
 
+def skeleton_golden():
+    """(f)2: skeleton_classifer/Models.py Transformer, built as test_emotion_gesture_diversity_iterative.py:158 does
+    (d_model 512, d_k = d_v = 64, n_position 60; pose_dim 282, d_inner 2048 = BEAT geometry)."""
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("torch_dct", types.ModuleType("torch_dct"))      # imported, never used (Models.py:8)
+    import importlib
+    kw = dict(class_dim=8, pose_dim=282, d_word_vec=512, d_model=512, d_inner=2048, n_layers=3, n_head=8, d_k=64, d_v=64,
+              n_position=60)
+    ref = importlib.import_module("skeleton_classifer.Models").Transformer(**kw).eval()
+    mine = mirrors.SkeletonClassifier(**kw)
+    same_layout(ref, mine)
+    sd = synth.synth_state_dict(mine.state_dict(), 17)
+    ref.load_state_dict(sd)
+    n = 3
+    poses = rnd((n, 60, 282), 17, 1)
+    with torch.no_grad():
+        r_logits, r_mid = ref(poses)
+        o_logits, o_mid = oa.skeleton_classifier(sd, poses)
+    print(f"  skeleton logits: oracle vs reference {rel(o_logits, r_logits):.2e}; mid_feature {rel(o_mid, r_mid):.2e}")
+    assert rel(o_logits, r_logits) <= 2e-6 and rel(o_mid, r_mid) <= 2e-6
+    np.savez_compressed(os.path.join(GOLD, "aux_skeleton.npz"), seed=17, n=n, logits=r_logits.numpy(),
+                        mid=r_mid.numpy().astype(np.float32))
+
+
 if __name__ == "__main__" and "--emotion-net" in sys.argv:
     emotion_net_golden()
+if __name__ == "__main__" and "--skeleton" in sys.argv:
+    skeleton_golden()

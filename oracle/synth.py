@@ -49,6 +49,10 @@ def synth_tensor(key: str, shape, seed: int, dtype=torch.float32, norm: bool = F
         a = r.uniform(-bound, bound, shape)
     else:
         a = r.uniform(-0.05, 0.05, shape)
+    if "temporal_chunk_encoder.2." in key:
+        # Models_memory.py:287-289 squares this encoding inside a softmax; at xavier scale the scores are +-100 and the
+        # softmax is a constant one-hot, which would leave the temporal memory arithmetic untested
+        a = a * 0.1
     return torch.tensor(a, dtype=dtype)
 
 

@@ -5,10 +5,13 @@ import numpy as np
 import torch
 
 from emotiongestures_b200 import BEAT, TED, Transformer
+from emotiongestures_b200.generator import MemoryTransformer
 from oracle import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CFGS = {"ted": TED, "beat": BEAT}
+# "tedmem": TED geometry with the Prior_MemoryEncoder of Full_model/Models_memory.py (args.chunk = 4)
+CFGS = {"ted": TED, "beat": BEAT, "tedmem": TED}
+MEM_CHUNK = 4
 _cache = {}
 
 
@@ -16,7 +19,8 @@ def model_and_sd(name: str, seed: int):
     """Mirror module (CPU) + the synthetic state_dict for (cfg, seed)."""
     key = (name, seed)
     if key not in _cache:
-        m = Transformer.from_config(CFGS[name]).eval()
+        m = (MemoryTransformer.from_config(CFGS[name], MEM_CHUNK) if name == "tedmem"
+             else Transformer.from_config(CFGS[name])).eval()
         sd = synth.synth_state_dict(m.state_dict(), seed)
         m.load_state_dict(sd)
         _cache[key] = (m, sd)

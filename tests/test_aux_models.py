@@ -38,6 +38,9 @@ CASES = {
     "pose_enc": (mirrors.PoseEncoderConv, 14, (60, 282)),
     "fgd_mlp": (mirrors.FGDNet, 15, ()),
     "emotion_net": (mirrors.EmotionNet, 16, ()),     # 1 GB of fp32 weights: built once per session
+    # skeleton_classifer Transformer as test_emotion_gesture_diversity_iterative.py:158 builds it (BEAT geometry):
+    # class_dim, pose_dim, src_pad, trg_pad, d_word_vec, d_model, d_inner, n_layers, n_head, d_k, d_v, dropout, n_position
+    "skeleton": (mirrors.SkeletonClassifier, 17, (8, 282, 1, 1, 512, 512, 2048, 3, 8, 64, 64, 0.2, 60)),
 }
 _big = {}
 
@@ -66,6 +69,9 @@ def reference_and_inputs(name):
     elif name == "pose_enc":
         ins = dict(poses=rnd((int(g["n"]), 60, 282), seed, 1))
         ref = {"mu": torch.from_numpy(g["mu"])}
+    elif name == "skeleton":
+        ins = dict(poses=rnd((int(g["n"]), 60, 282), seed, 1))
+        ref = {"logits": torch.from_numpy(g["logits"]), "mid": torch.from_numpy(g["mid"])}
     else:
         ins = dict(poses=rnd((int(g["n"]), 60, 282), seed, 1))
         ref = {"latent": torch.from_numpy(g["latent"])}
@@ -85,6 +91,9 @@ def oracle_outputs(name, sd, ins):
             return {"mu": oa.pose_encoder(sd, ins["poses"], "", fc_mu=True)}
         if name == "emotion_net":
             return {"logits": oa.emotion_net(sd, ins["mfcc"])}
+        if name == "skeleton":
+            logits, mid = oa.skeleton_classifier(sd, ins["poses"])
+            return {"logits": logits, "mid": mid}
         return {"latent": oa.fgd_latent(sd, ins["poses"])}
 
 
@@ -131,6 +140,9 @@ def device_outputs(name, m, ins):
             return {"mu": m(d["poses"], False)[1]}
         if name == "emotion_net":
             return {"logits": m(d["mfcc"])}
+        if name == "skeleton":
+            logits, mid = m(d["poses"])
+            return {"logits": logits, "mid": mid}
         return {"latent": m(d["poses"])[1]}
 
 
@@ -139,7 +151,7 @@ def device_outputs(name, m, ins):
 def test_cuda_matches_reference_golden(name):
     m, _, ins, ref = reference_and_inputs(name)
     got = device_outputs(name, m, ins)
-    tol = {"fgd_mlp": 2e-3, "emotion_net": 2e-3}.get(name, 2e-5)
+    tol = {"fgd_mlp": 2e-3, "emotion_net": 2e-3, "skeleton": 2e-3}.get(name, 2e-5)
     for k, r in ref.items():
         g = got[k].cpu()
         assert g.shape == r.shape and not torch.isnan(g).any()
@@ -148,7 +160,7 @@ def test_cuda_matches_reference_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n", [("cvae", 1), ("cvae", 1000), ("motion_ae", 300), ("pose_enc", 150), ("cvae3", 150),
-                                    ("fgd_mlp", 77)])
+                                    ("fgd_mlp", 77), ("skeleton", 1), ("skeleton", 77)])
 def test_cuda_matches_oracle_at_ragged_sizes(name, n):
     """Sizes that do not divide the kernels' tiles / exceed one wave, against the oracle on the same inputs."""
     cls, seed, args = CASES[name]
@@ -163,7 +175,7 @@ def test_cuda_matches_oracle_at_ragged_sizes(name, n):
         ins = dict(poses=rnd((n, 60, 282), n, 1))
     ref = oracle_outputs(name, oa.cast(sd, torch.float64), {k: v.double() for k, v in ins.items()})
     got = device_outputs(name, m, ins)
-    tol = 2e-3 if name == "fgd_mlp" else 2e-5
+    tol = 2e-3 if name in ("fgd_mlp", "skeleton") else 2e-5
     for k, r in ref.items():
         assert rel_max(got[k].cpu(), r) <= tol, (name, k, rel_max(got[k].cpu(), r))
 
@@ -177,3 +189,11 @@ def test_cuda_empty_batches_and_shape_errors():
     enc = enc.cuda()
     with pytest.raises(RuntimeError, match="does not match"):
         enc(torch.zeros(2, 60, 126, device="cuda"))
+    sk, _ = build(*[CASES["skeleton"][0], 3, *CASES["skeleton"][2]])
+    sk = sk.cuda()
+    logits, mid = sk(torch.zeros(0, 60, 282, device="cuda"))
+    assert logits.shape == (0, 8) and mid.shape == (0, 60, 512)
+    with pytest.raises(RuntimeError, match="do not match"):
+        sk(torch.zeros(2, 34, 282, device="cuda"))            # post_projector flattens exactly n_position frames
+    with pytest.raises(RuntimeError, match="d_k = d_v = 64"):
+        mirrors.SkeletonClassifier().eval().cuda()(torch.zeros(1, 60, 242, device="cuda"))   # reference defaults: d_k = 32

@@ -73,7 +73,7 @@ def test_trunk_stages_match_oracle(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
-@pytest.mark.parametrize("gold", ["ted_b2", "ted_b2_emotion", "beat_b1"])
+@pytest.mark.parametrize("gold", ["ted_b2", "ted_b2_emotion", "beat_b1", "tedmem_b3"])
 def test_forward_matches_reference_golden(gold, precision):
     g = load_golden(gold)
     name = gold.split("_")[0]
@@ -114,6 +114,23 @@ def test_forward_matches_oracle_ragged_batches(precision):
         assert torch.equal(part, full[lo:hi]), "per-clip result depends on the clip's position in the batch"
     empty = eng.generator_forward(spec[:0], prior[:0])[0]
     assert empty.shape == (0, TED.frames, TED.pose_dim)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_memory_variant_matches_oracle_at_ragged_batches(precision):
+    """Prior_MemoryEncoder (Models_memory.py): batch sizes around the kernels' tiles; the temporal memory's batch sum
+    makes every size its own problem, so each is compared with the oracle on the same batch."""
+    eng, sd = _engine("tedmem", 9, precision)
+    for n in (1, 2, 37):
+        spec, prior, _ = inputs(TED, n, seed=30 + n)
+        with torch.no_grad():
+            ref = og.generator_forward(sd, TED, spec, prior)
+        poses = eng.generator_forward(spec, prior)[0].cpu()
+        assert rel_fro(poses, ref[0]) <= TOL[precision], (n, rel_fro(poses, ref[0]))
+        taps = og.Taps()
+        assert rel_fro(eng.tap("prior_feature").cpu(), og.prior_memory_encoder(sd, prior)) <= TOL[precision]
+    again = eng.generator_forward(spec, prior)[0].cpu()
+    assert torch.equal(again, poses), "same batch must give the same bits (fixed-order batch sum)"
 
 
 def test_module_forward_and_audio_entry():

@@ -11,7 +11,7 @@ from oracle import generator as og
 from tests.helpers import CFGS, inputs, load_golden, model_and_sd, rel_max
 
 
-@pytest.mark.parametrize("gold", ["ted_b2", "ted_b2_emotion", "beat_b1"])
+@pytest.mark.parametrize("gold", ["ted_b2", "ted_b2_emotion", "beat_b1", "tedmem_b3"])
 def test_oracle_reproduces_reference_golden(gold):
     g = load_golden(gold)
     name = gold.split("_")[0]
@@ -47,6 +47,29 @@ def test_state_dict_layout_is_the_reference_one():
     mb, sdb = model_and_sd("beat", 1)
     assert sdb["audio_encoder.fc1.weight"].shape == (512, 32 * 31)
     assert sum(v.numel() for v in sdb.values() if v.is_floating_point()) > 46_000_000
+
+
+def test_memory_prior_encoder_structure():
+    """Full_model/Models_memory.py:335-345: the first prior_frames rows of the encoder input are the prior poses
+    themselves, so their features do not depend on the memory nets (nor, through TM_Memory_Net's
+    memory_encoding.t() @ pred_encoding batch sum, :287-288, on the clip's batch mates); only rows
+    p .. p+chunk-1 see the spatial / temporal memory."""
+    _, sd = model_and_sd("tedmem", 5)
+    _, prior, _ = inputs(TED, 3, 5)
+    p = TED.prior_frames
+    with torch.no_grad():
+        full = og.prior_memory_encoder(sd, prior)
+        alone = og.prior_memory_encoder(sd, prior[:1])
+        head = og._linear(sd, "prior_seq_encoder.post_header.2", og._linear(sd, "prior_seq_encoder.post_header.0", prior))
+        sd2 = dict(sd)
+        k = "prior_seq_encoder.temporal_memory.temporal_chunk_encoder.2.bias"
+        sd2[k] = sd[k] + 1.0
+        moved = og.prior_memory_encoder(sd2, prior)
+    assert full.shape == (3, TED.frames, TED.d_model)
+    assert torch.allclose(full[:, :p], head, atol=1e-6) and torch.allclose(alone[0, :p], full[0, :p], atol=1e-6)
+    from tests.helpers import MEM_CHUNK
+    assert torch.equal(moved[:, p + MEM_CHUNK:], full[:, p + MEM_CHUNK:])      # frames past the chunk are untouched
+    assert not torch.equal(moved[:, p:p + MEM_CHUNK], full[:, p:p + MEM_CHUNK])
 
 
 def test_structural_invariants():
