@@ -2,6 +2,7 @@
 
 Public surface:
   Transformer            drop-in for Full_model.Models.Transformer (inference)
+  MemoryTransformer      drop-in for Full_model.Models_memory.Transformer (Prior_MemoryEncoder variant)
   install(generator)     swap a live reference generator's forward for libegx
   Engine                 thin object wrapper over the C ABI (include/egx.h)
   GeneratorConfig, TED, BEAT
@@ -9,9 +10,9 @@ Public surface:
 """
 from .config import (BEAT, LOGMEL_DB, LOGMEL_LOG_IN, TED, GeneratorConfig, audio_length,
                      spectrogram_length)
-from .generator import Transformer, randomize_norm_stats_
+from .generator import MemoryTransformer, Transformer, randomize_norm_stats_
 
-__all__ = ["Transformer", "install", "Engine", "GeneratorConfig", "TED", "BEAT", "LOGMEL_DB",
+__all__ = ["Transformer", "MemoryTransformer", "install", "Engine", "GeneratorConfig", "TED", "BEAT", "LOGMEL_DB",
            "LOGMEL_LOG_IN", "audio_length", "spectrogram_length", "randomize_norm_stats_"]
 
 

@@ -22,7 +22,11 @@ from .engine import Engine
 def config_from_module(gen) -> GeneratorConfig:
     sd = gen.state_dict()
     d_model = sd["emotion_proj.0.weight"].shape[0]
-    frames, prior_frames, _ = sd["prior_seq_encoder.conv1.weight"].shape
+    if "prior_seq_encoder.pred_conv.0.weight" in sd:        # Models_memory.Transformer: conv maps p -> F - p frames
+        n_pred, prior_frames, _ = sd["prior_seq_encoder.pred_conv.0.weight"].shape
+        frames = n_pred + prior_frames
+    else:
+        frames, prior_frames, _ = sd["prior_seq_encoder.conv1.weight"].shape
     pose_dim = sd["post_projector.6.weight"].shape[0]
     fc1_in = sd["audio_encoder.fc1.weight"].shape[1]
     n_layers = len(gen.encoder.layer_stack)

@@ -221,6 +221,7 @@ class _MHA(nn.Module):
 
     def __init__(self, n_head, d_model, d_k, d_v):
         super().__init__()
+        self.n_head, self.d_k, self.d_v = n_head, d_k, d_v
         self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
         self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
         self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)

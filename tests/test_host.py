@@ -75,3 +75,16 @@ def test_shard_bounds_partition_the_batch():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(8, 2, 2)
+
+
+def test_dropin_reads_the_geometry_of_both_generator_variants():
+    """install() derives egx_cfg from a live module's state_dict: Models.Transformer and Models_memory.Transformer
+    (whose prior conv maps p -> F - p frames, Full_model/Models_memory.py:321-329)."""
+    from emotiongestures_b200 import BEAT, TED, MemoryTransformer, Transformer
+    from emotiongestures_b200.dropin import config_from_module
+    for cfg, m in ((TED, Transformer.from_config(TED)), (BEAT, Transformer.from_config(BEAT)),
+                   (TED, MemoryTransformer.from_config(TED, 4)), (BEAT, MemoryTransformer.from_config(BEAT, 10))):
+        got = config_from_module(m)
+        for f in ("frames", "prior_frames", "pose_dim", "d_model", "d_inner", "n_layers", "n_head", "d_k", "d_v", "spec_w",
+                  "n_position"):
+            assert getattr(got, f) == getattr(cfg, f), (type(m).__name__, f)
