@@ -8,9 +8,11 @@
 // FFT done as a 512-point complex FFT: three radix-8 Stockham passes whose butterflies live in
 // registers (16 points per lane) and exchange through one padded, conflict-free shared-memory
 // buffer per warp (fp32, twiddles from a float64-built table), followed by the real-FFT untangling,
-// the sparse mel projection (<= 24 taps per mel) and the log.  The clip's (128, W) tile stays
-// in shared memory until the per-(clip, mel) statistics are known, so the audio is read once
-// and the log-mel written once: algorithmic HBM traffic 4*N + 4*128*W bytes per clip.
+// the sparse mel projection (<= 24 taps per mel) and the log.  The raw log values go straight to the
+// output tile; once the CTA has written all of it, the per-(clip, mel) statistics are taken from that
+// tile (still in L2, 36 KB per clip) and it is normalised in place.  Keeping the tile out of shared
+// memory lets three CTAs share an SM (the kernel is latency-bound: every FFT pass is a shared-memory
+// round trip).  Algorithmic HBM traffic 4*N + 4*128*W bytes per clip.
 #include "egx_common.cuh"
 
 namespace egx {
@@ -21,7 +23,7 @@ constexpr int kFFT = 1024;
 constexpr int kHalf = 512;       // complex FFT length
 constexpr int kHop = 512;
 constexpr int kMels = 128;
-constexpr int kWarps = 16;
+constexpr int kMaxWarps = 12;      // 384 threads x 3 CTAs per SM at <= 56 registers
 constexpr int kBufLen = kHalf + kHalf / 8;     // padded: physical index i + (i >> 3)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -85,39 +87,70 @@ __device__ __forceinline__ void fft_pass(float2* buf, int lane, const float2* __
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+// raw samples of 8 of the 16 complex points of this lane: point n = lane + 32 (i0 + i) holds samples (base + 2n, base + 2n + 1)
+template <bool kAligned>
+__device__ __forceinline__ void load_frame(const float* __restrict__ x, int N, int base, int lane, int i0, float (&r0)[8], float (&r1)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int s0 = base + 2 * (lane + 32 * (i0 + i));
+        r0[i] = 0.f; r1[i] = 0.f;
+        if (s0 >= 0 && s0 + 1 < N) {
+            if (kAligned) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(x + s0));
+                r0[i] = v.x; r1[i] = v.y;
+            } else {
+                r0[i] = __ldg(x + s0); r1[i] = __ldg(x + s0 + 1);
+            }
+        } else if (s0 >= 0 && s0 < N) {
+            r0[i] = __ldg(x + s0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMaxWarps * 32, 3)
 logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int preemph,
               float* __restrict__ out, const float* __restrict__ window,
               const float2* __restrict__ tw512, const float2* __restrict__ tw1024,
               const int* __restrict__ mel_start, const int* __restrict__ mel_ptr,
               const float* __restrict__ mel_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                 // [kWarps][kBufLen]
-    float* tile = reinterpret_cast<float*>(fftbuf + kWarps * kBufLen);    // [128][n_cols]
-    __shared__ float s_red[kWarps];
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                 // [warps][kBufLen]
+    __shared__ float s_red[kMaxWarps];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const float* x = audio + (size_t)blockIdx.x * N;
     float2* buf = fftbuf + warp * kBufLen;
+    float* tile = out + (size_t)blockIdx.x * kMels * n_cols;             // raw log values, normalised in place below
+    // 8-byte loads need the clip's first sample on an even float (N may be odd): uniform per CTA
+    const bool aligned = (((size_t)blockIdx.x * N) & 1) == 0 && (reinterpret_cast<uintptr_t>(audio) & 7) == 0;
 
-    for (int t = warp; t < n_cols; t += kWarps) {
+    for (int t = warp; t < n_cols; t += n_warps) {
         // ---- framing + pre-emphasis + window; even/odd samples of the frame form one complex point ----
+        // all 32 loads of the lane are issued before the first use; x[s0 - 1] comes from the neighbouring lane
         const int base = t * kHop - kFFT / 2;
-#pragma unroll 4
-        for (int n = lane; n < kHalf; n += 32) {
-            const int s0 = base + 2 * n;
-            const float xm = (s0 - 1 >= 0 && s0 - 1 < N) ? x[s0 - 1] : 0.f;
-            float x0 = (s0 >= 0 && s0 < N) ? x[s0] : 0.f;
-            float x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? x[s0 + 1] : 0.f;
+        float carry = 0.f;                             // x1 of lane 31 of the previous 32-point group
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 8) {
+        float r0[8], r1[8];
+        if (aligned) load_frame<true>(x, N, base, lane, i0, r0, r1);
+        else load_frame<false>(x, N, base, lane, i0, r0, r1);
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+            const int i = i0 + ii, n = lane + 32 * i, s0 = base + 2 * n;
+            float x0 = r0[ii], x1 = r1[ii];
             if (preemph) {
                 // y[t] = x[t] - 0.97 x[t-1], x[-1] := x[1] (reflect pad of 1); samples outside the clip stay zero
+                float xm = __shfl_up_sync(0xffffffffu, r1[ii], 1);
+                if (lane == 0) xm = i ? carry : ((s0 - 1 >= 0 && s0 - 1 < N) ? __ldg(x + s0 - 1) : 0.f);
+                carry = __shfl_sync(0xffffffffu, r1[ii], 31);
                 const float y1 = x1 - 0.97f * x0;
-                const float y0 = x0 - 0.97f * (s0 == 0 ? x[1] : xm);
+                const float y0 = x0 - 0.97f * (s0 == 0 ? r1[ii] : xm);
                 x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? y1 : 0.f;
                 x0 = (s0 >= 0 && s0 < N) ? y0 : 0.f;
             }
-            const float2 w = *reinterpret_cast<const float2*>(window + 2 * n);
+            const float2 w = __ldg(reinterpret_cast<const float2*>(window + 2 * n));
             buf[pad(n)] = make_float2(x0 * w.x, x1 * w.y);
+        }
         }
         __syncwarp();
         // ---- 512-point complex FFT: three radix-8 Stockham passes ----
@@ -162,12 +195,12 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
         }
         __syncwarp();
     }
-    __syncthreads();
+    __syncthreads();        // CTA-scope visibility of the tile written above (global memory, same CTA)
 
-    float* o = out + (size_t)blockIdx.x * kMels * n_cols;
+    float* o = tile;
     if (mode == EGX_LOGMEL_LOG_IN) {
         // InstanceNorm1d: per (clip, mel) over time, biased variance, eps 1e-5, no affine
-        for (int m = warp; m < kMels; m += kWarps) {
+        for (int m = warp; m < kMels; m += n_warps) {
             const float* row = tile + m * n_cols;
             float s = 0.f;
             for (int t = lane; t < n_cols; t += 32) s += row[t];
@@ -185,8 +218,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
         if (lane == 0) s_red[warp] = mx;
         __syncthreads();
         mx = s_red[0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) mx = fmaxf(mx, s_red[w]);
+        for (int w = 1; w < n_warps; ++w) mx = fmaxf(mx, s_red[w]);
         for (int i = threadIdx.x; i < kMels * n_cols; i += blockDim.x)
             o[i] = fmaxf(tile[i] - mx, -80.f);
     }
@@ -196,14 +228,18 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
 
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
                   int preemph, float* out, cudaStream_t s) {
-    const size_t smem = sizeof(float2) * kWarps * kBufLen + sizeof(float) * kMels * n_cols;
+    // warps per CTA: the count in [9, 12] that wastes the fewest warp slots in the last round of frames
+    int warps = kMaxWarps;
+    for (int w = kMaxWarps; w >= 9; --w)
+        if ((n_cols + w - 1) / w * w < (n_cols + warps - 1) / warps * warps) warps = w;
+    const size_t smem = sizeof(float2) * warps * kBufLen;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess) return -1;
         configured = smem;
     }
-    logmel_kernel<<<B, kWarps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window,
+    logmel_kernel<<<B, warps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window,
                                                 t.tw512, t.tw1024, t.mel_start, t.mel_ptr,
                                                 t.mel_w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
