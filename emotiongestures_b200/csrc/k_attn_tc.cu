@@ -56,12 +56,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     unsigned char* sV = sK + kKVBytes;
     unsigned char* sP = sV + kKVBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
-    uint64_t* full = bars;          // Q/K/V landed
-    uint64_t* empty = bars + 1;     // Q/K/V consumed (both MMAs done)
+    // Q/K and V have separate barriers: Q and K are free again as soon as the score MMAs are done, so the next
+    // tile's Q/K loads (the DRAM latency of the chain) run under this tile's softmax, P.V and output
+    uint64_t* full_qk = bars;       // Q, K landed
+    uint64_t* empty_qk = bars + 1;  // Q, K consumed (score MMAs done)
     uint64_t* s_full = bars + 2;    // scores in TMEM
     uint64_t* p_full = bars + 3;    // P in smem
     uint64_t* o_full = bars + 4;    // output accumulator in TMEM
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* full_v = bars + 5;    // V landed
+    uint64_t* empty_v = bars + 6;   // V consumed (P.V MMAs done)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = p.G * p.L;
@@ -70,7 +74,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmQ);
         prefetch_tmap(&tmKV);
-        mbar_init(full, 1); mbar_init(empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+        mbar_init(full_qk, 1); mbar_init(empty_qk, 1); mbar_init(full_v, 1); mbar_init(empty_v, 1);
+        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(tmem_ptr);
@@ -88,18 +93,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
-            const uint32_t bytes = 3u * rows * 128u;
+            const uint32_t bytes = rows * 128u;
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int g = tile / p.n_head, h = tile % p.n_head;
                 const int row0 = g * rows;
-                mbar_wait(empty, (it & 1) ^ 1);
-                mbar_expect_tx(full, bytes);
-                tma_load_2d(sQ, &tmQ, full, p.q_col0 + h * 64, row0);
-                for (int cl = 0; cl < p.G; ++cl) {        // one box per clip, landing on its 16-aligned key slot
-                    tma_load_2d(sK + cl * p.LP * 128, &tmKV, full, p.k_col0 + h * 64, row0 + cl * p.L);
-                    tma_load_2d(sV + cl * p.LP * 128, &tmKV, full, p.v_col0 + h * 64, row0 + cl * p.L);
-                }
+                mbar_wait(empty_qk, (it & 1) ^ 1);
+                mbar_expect_tx(full_qk, 2 * bytes);
+                tma_load_2d(sQ, &tmQ, full_qk, p.q_col0 + h * 64, row0);
+                for (int cl = 0; cl < p.G; ++cl)          // one box per clip, landing on its 16-aligned key slot
+                    tma_load_2d(sK + cl * p.LP * 128, &tmKV, full_qk, p.k_col0 + h * 64, row0 + cl * p.L);
+                mbar_wait(empty_v, (it & 1) ^ 1);
+                mbar_expect_tx(full_v, bytes);
+                for (int cl = 0; cl < p.G; ++cl)
+                    tma_load_2d(sV + cl * p.LP * 128, &tmKV, full_v, p.v_col0 + h * 64, row0 + cl * p.L);
             }
         }
     } else if (warp == 1) {
@@ -109,18 +116,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const uint32_t q = smem_u32(sQ), k = smem_u32(sK), v = smem_u32(sV), pp = smem_u32(sP);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(full, it & 1);
+                mbar_wait(full_qk, it & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_f16(tmem_S, make_smem_desc<128>(q + kk * 32), make_smem_desc<128>(k + kk * 32), idesc_s, kk != 0);
+                umma_commit(empty_qk);
                 umma_commit(s_full);
                 mbar_wait(p_full, it & 1);
+                mbar_wait(full_v, it & 1);
                 tc_fence_after();
                 for (int kk = 0; kk < p.NK / 16; ++kk)
                     umma_f16(tmem_O, make_smem_desc<128>(pp + (kk >> 2) * kTileBytes + (kk & 3) * 32),
                              make_desc_mn128(v + kk * 2048), idesc_o, kk != 0);
-                umma_commit(empty);
+                umma_commit(empty_v);
                 umma_commit(o_full);
             }
         }
@@ -149,9 +158,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 float v[16];
                 __syncwarp();
                 tmem_ld16(tmem_S + lane_addr + c, v);
+                if (!row_used || c < c_lo || c >= c_hi) continue;              // not this row's key slot (16-aligned)
+                if (c + 16 <= c_hi) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c + j >= c_lo && c + j < c_hi) mx = fmaxf(mx, v[j]);
+                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < c_hi) mx = fmaxf(mx, v[j]);
+                }
             }
             // pass 2: p = exp((s - max) / sqrt(d_k)), zeros elsewhere, fp16 into the swizzled A-operand layout
             float sum = 0.f;
@@ -161,11 +176,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 __syncwarp();
                 tmem_ld16(tmem_S + lane_addr + c, v);
                 if (!row_used || c < c_lo || c >= c_lo + p.LP) continue;      // not this row's key slot (16-aligned)
+                const float mxs = mx * p.scale_log2e;
+                if (c + 16 <= c_hi) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float e = c + j < c_hi ? exp2f((v[j] - mx) * p.scale_log2e) : 0.f;
-                    v[j] = e;
-                    sum += e;
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = exp2f(fmaf(v[j], p.scale_log2e, -mxs));
+                        sum += v[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float e = c + j < c_hi ? exp2f(fmaf(v[j], p.scale_log2e, -mxs)) : 0.f;
+                        v[j] = e;
+                        sum += e;
+                    }
                 }
 #pragma unroll
                 for (int j8 = 0; j8 < 2; ++j8) {
@@ -195,14 +219,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 __syncwarp();
                 tmem_ld32(tmem_O + lane_addr + c, v);
                 if (store) {
+                    if (((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.ldo * 2)) & 31) == 0) {
+                        // 256-bit stores: every instruction writes whole 32-byte sectors
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j] * inv, v[8 * j + 1] * inv);
-                        *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[8 * j + 2] * inv, v[8 * j + 3] * inv);
-                        *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(v[8 * j + 4] * inv, v[8 * j + 5] * inv);
-                        *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(v[8 * j + 6] * inv, v[8 * j + 7] * inv);
-                        reinterpret_cast<uint4*>(o + c)[j] = u;
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t u[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const __half2 h2 = __floats2half2_rn(v[16 * j + 2 * e] * inv, v[16 * j + 2 * e + 1] * inv);
+                                u[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + c + 16 * j),
+                                         "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                                         : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v[8 * j] * inv, v[8 * j + 1] * inv);
+                            *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v[8 * j + 2] * inv, v[8 * j + 3] * inv);
+                            *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(v[8 * j + 4] * inv, v[8 * j + 5] * inv);
+                            *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(v[8 * j + 6] * inv, v[8 * j + 7] * inv);
+                            reinterpret_cast<uint4*>(o + c)[j] = u;
+                        }
                     }
                 }
             }

@@ -81,7 +81,7 @@ struct ConvCfg {
     static constexpr int kNumKb = TAPS * kChunks;            // K blocks per tile
     static constexpr int kABytes = 128 * kSwz;
     static constexpr int kBBytes = ((NPAD * kSwz + 1023) / 1024) * 1024;
-    static constexpr bool kResidentB = kNumKb * kBBytes <= 80 * 1024;
+    static constexpr bool kResidentB = kNumKb * kBBytes <= (HALO ? 112 : 80) * 1024;
     // K blocks handled per pipeline stage (one barrier round-trip): keep >= 4 MMAs of work per wait
     static constexpr int kKbPerStage = HALO ? kNumKb : ((CK == 32 && TAPS == 9) ? 3 : 1);
     static constexpr int kPatchBytes = kPatchRows * kSwz;
@@ -878,7 +878,7 @@ int g_num_sms = 0;
 int g_debug = 0;
 int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
 int g_contig = 0;    // EGX_CONV_CONTIG: 1 = contiguous tile runs per CTA, 0 = strided walk (default: measured faster, the CTAs share halos in L2)
-int g_halo = 7;      // EGX_CONV_HALO: 0 = off, 1 = 64->64 convs (default), 2 = also 32->32
+int g_halo = 7;       // EGX_CONV_HALO bits: 1 = 64->64 convs, 2 = 32->32, 4 = 128->128, 8 = final conv (128 -> <= 48, NCHW out)
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT, int MODE>
 int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s,
@@ -983,7 +983,7 @@ int set_attr() {
     X(64, 128, 9, false, OUT_DIRECT) X(64, 128, 1, false, OUT_DIRECT) X(128, 128, 9, false, OUT_DIRECT) \
     X(32, 32, 9, true, OUT_DIRECT) X(64, 64, 9, true, OUT_DIRECT)                                     \
     X(256, 128, 9, false, OUT_DIRECT) X(128, 128, 1, false, OUT_DIRECT)                               \
-    X(128, 48, 9, false, OUT_NCHW) X(128, 64, 9, false, OUT_NCHW)
+    X(128, 48, 9, false, OUT_NCHW) X(128, 64, 9, false, OUT_NCHW) X(128, 48, 9, true, OUT_NCHW)
 
 // conv1 of an SE block (sums its output): stride-1 halo kernels, the stride-2 first blocks of a stage, 256-wide slices
 #define EGX_CONV_SE_INSTANCES(X)                                                                       \
@@ -1022,6 +1022,8 @@ int conv_tc_init_device() {
 }
 
 static bool use_halo(int cin, int cout, int ks, int stride, int nchw) {
+    // final conv of the TED generator (128 -> 34 frames, N padded to 48): 108 KB of weights stay resident
+    if (ks == 3 && stride == 1 && nchw && cin == 128 && cout <= 48 && (g_halo & 8)) return true;
     if (ks != 3 || stride != 1 || nchw || cin != cout) return false;
     return (cin == 64 && g_halo >= 1) || (cin == 32 && (g_halo & 2)) || (cin == 128 && (g_halo & 4));
 }
@@ -1043,7 +1045,7 @@ int launch_conv_tc(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     const int npad = c.cout <= 32 ? 32 : (c.cout <= 48 ? 48 : (c.cout <= 64 ? 64 : 128));
     if ((c.cout > 128 && (nchw || c.cout % 128)) || (!nchw && c.cout % 32)) return -1;
     const bool halo = use_halo(c.cin, c.cout, c.ks, c.stride, nchw);
-    if (halo && c.cin == 128) return launch_conv128(c, in, B, Hin, Win, out, se_part, s, gate, res);
+    if (halo && c.cin == 128 && !nchw) return launch_conv128(c, in, B, Hin, Win, out, se_part, s, gate, res);
     const int out_mode = nchw ? OUT_NCHW : ((npad <= 64 && !(halo && ((c.cin == 32 && (g_out_direct & 1)) || (c.cin == 64 && (g_out_direct & (gate ? 4 : 2)))))) ? OUT_TMA : OUT_DIRECT);
 #define X_MODE(CI, NP, TP, HL, OU, MD)                                                          \
     if (c.cin == CI && npad == NP && c.ks * c.ks == TP && halo == HL && out_mode == OU && mode == MD) \
