@@ -188,21 +188,26 @@ class Engine:
             }
         c = st["chunk"]
         main = torch.cuda.current_stream(dev)
-        start = torch.cuda.Event()
-        start.record(main)
-        st["h2d"].wait_event(start)
-        st["d2h"].wait_event(start)
-        for i, lo in enumerate(range(0, b, c)):
-            hi, slot = min(lo + c, b), i & 1
+        # chunk bounds: a short first chunk (its host->device copy is the only one nothing can hide), then full ones
+        bounds, lo = [], 0
+        while lo < b:
+            hi = min(b, lo + (max(1, c // 4) if lo == 0 and b > c else c))
+            bounds.append((lo, hi))
+            lo = hi
+        used = st.setdefault("used", [False, False])
+        for i, (lo, hi) in enumerate(bounds):
+            slot = (st.get("next_slot", 0) + i) & 1
             n = hi - lo
             with torch.cuda.stream(st["h2d"]):
-                if i >= 2:
+                # the inputs are pinned HOST memory, already final when this call is made: the copy only has to wait
+                # for the staging slot, so the first copy of a call overlaps the tail of the previous call's kernels
+                if used[slot]:
                     st["h2d"].wait_event(st["in_free"][slot])
                 st["audio"][slot][:n].copy_(audio_h[lo:hi], non_blocking=True)
                 st["prior"][slot][:n].copy_(prior_h[lo:hi], non_blocking=True)
                 st["ready"][slot].record(st["h2d"])
             main.wait_event(st["ready"][slot])
-            if i >= 2:
+            if used[slot]:
                 main.wait_event(st["out_free"][slot])
             spec = self.logmel(st["audio"][slot][:n], mode, preemph)
             out = tuple(t[:n] for t in st["out"][slot])
@@ -215,6 +220,8 @@ class Engine:
                 st["d2h"].wait_event(st["done"][slot])
                 poses_h[lo:hi].copy_(out[0], non_blocking=True)
                 st["out_free"][slot].record(st["d2h"])
+            used[slot] = True
+        st["next_slot"] = (st.get("next_slot", 0) + len(bounds)) & 1
         main.wait_stream(st["d2h"])
         return poses_h
 
