@@ -183,3 +183,30 @@ def test_infer_host_pipeline_matches_single_shot():
     eng.infer_host(audio, prior, poses_h, chunk=8)          # slots are reused across calls
     torch.cuda.synchronize()
     assert torch.equal(poses_h, ref)
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json config 2 (4096 TED clips on one GPU), through size-independent properties: at this size the
+    persistent kernels run many tiles per CTA and the Linear layers take the weights-resident GEMM variant, which
+    small batches never reach.  (1) the same batch gives the same bits twice; (2) every clip's poses equal, bit for
+    bit, what the same clip gives in a 7-clip batch (oracle-checked sizes), wherever it sits in the big batch;
+    (3) the log-mel of the big batch equals the small-batch one; (4) a sample of clips agrees with the oracle."""
+    eng, sd = _engine("ted", 0, "tc")
+    n = 4096
+    g = torch.Generator().manual_seed(77)
+    audio = (0.1 * torch.randn(n, TED.n_audio, generator=g)).clamp_(-1, 1).cuda()
+    prior = torch.randn(n, TED.prior_frames, TED.pose_dim, generator=g).cuda()
+    spec = eng.logmel(audio, LOGMEL_LOG_IN, True)
+    poses = eng.generator_forward(spec, prior)[0].clone()
+    again = eng.generator_forward(spec, prior)[0]
+    assert torch.equal(poses, again), "full-size forward is not deterministic"
+    assert torch.isfinite(poses).all()
+    for lo in (0, 1021, 2048, n - 7):
+        small_spec = eng.logmel(audio[lo:lo + 7], LOGMEL_LOG_IN, True)
+        assert torch.equal(small_spec, spec[lo:lo + 7]), "log-mel depends on the batch"
+        small = eng.generator_forward(small_spec, prior[lo:lo + 7])[0]
+        assert torch.equal(small, poses[lo:lo + 7]), f"clips {lo}..{lo + 6}: poses depend on batch size / position"
+    idx = [0, 1500, n - 1]
+    with torch.no_grad():
+        ref = og.generator_forward(sd, TED, spec[idx].cpu(), prior[idx].cpu())[0]
+    assert rel_fro(poses[idx].cpu(), ref) <= TOL["tc"]
