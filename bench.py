@@ -265,6 +265,26 @@ def run_own_arm(args):
     h2d = h_audio.numel() * 4 + h_prior.numel() * 4
     d2h = h_poses.numel() * 4
 
+    # ---- small batches are launch-bound: eager launches vs one CUDA-graph replay (Engine.capture), 1 and 8 clips ----
+    small = None
+    if rank == 0 and world == 1:
+        small = {}
+        for nb in (1, 8):
+            a, p_ = audio[:nb].contiguous(), prior[:nb].contiguous()
+            path = eng.capture(nb)
+            res = {}
+            for name, fn in (("eager", lambda: step(a, p_)), ("graph", lambda: path(a, p_))):
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(100):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res[name + "_ms"] = e0.elapsed_time(e1) / 100
+            small["clips_%d" % nb] = res
+
     if rank == 0:
         peaks = load_peaks()
         per_stage = {}
@@ -314,6 +334,7 @@ def run_own_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "Engine.infer_host (pinned host in/out, %d-clip chunks, copies overlapped)" % args.e2e_chunk},
             "gpu_launches": launches, "roofline": roofline, "stages": per_stage, "cpu_baseline": cpu,
+            "small_batch_latency": small,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -225,6 +225,15 @@ class Engine:
         main.wait_stream(st["d2h"])
         return poses_h
 
+    def capture(self, n_clips: int, mode: int = LOGMEL_LOG_IN, preemph: bool = True, with_emotion: bool = False):
+        """CUDA-graph the whole path (log-mel + generator forward, ~130 launches) for a fixed batch size.
+
+        Small batches are launch-bound: a 1-clip forward is ~130 kernels of a few microseconds each.  The returned
+        `GraphedPath` owns static input / output / workspace buffers and replays everything with one
+        cudaGraphLaunch; call it with (audio, prior[, sampled_emotion]) and it returns its static
+        (poses, emotion_feature, semantic_feature, emotion_logits) tensors (clone them to keep them)."""
+        return GraphedPath(self, n_clips, mode, preemph, with_emotion)
+
     # -- parity probes (tests) ----------------------------------------------------
     def tap(self, name: str):
         b = self._last_b
@@ -318,3 +327,50 @@ class Engine:
             self._check(self.lib.egx_fgd_accumulate(self._h, _ptr(f), n, d, _ptr(shift), _ptr(acc),
                                                     self._stream()), "egx_fgd_accumulate")
         return acc
+
+
+class GraphedPath:
+    """Fixed-batch CUDA graph over egx_logmel + egx_generator_forward (see Engine.capture)."""
+
+    def __init__(self, eng: Engine, n_clips: int, mode: int, preemph: bool, with_emotion: bool):
+        cfg, dev = eng.cfg, eng.device
+        self.eng, self.n = eng, int(n_clips)
+        n = self.n
+        self.audio = torch.zeros((n, cfg.n_audio), device=dev)
+        self.prior = torch.zeros((n, cfg.prior_frames, cfg.pose_dim), device=dev)
+        self.sampled = torch.zeros((n, cfg.frames, cfg.d_model), device=dev) if with_emotion else None
+        self.spec = torch.empty((n, cfg.n_mels, cfg.spec_w), device=dev)
+        self.out = (torch.empty((n, cfg.frames, cfg.pose_dim), device=dev), torch.empty((n, cfg.frames, cfg.d_model), device=dev),
+                    torch.empty((n, cfg.frames, cfg.d_model), device=dev), torch.empty((n, 8), device=dev))
+        # a private workspace: the engine's shared one may be re-allocated when a larger batch comes along
+        self.ws = torch.empty(int(eng.lib.egx_workspace_bytes(eng._h, n)), dtype=torch.uint8, device=dev)
+        self._mode, self._preemph = int(mode), int(bool(preemph))
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._enqueue()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+
+    def _enqueue(self):
+        eng, cfg, n = self.eng, self.eng.cfg, self.n
+        with torch.cuda.device(eng.device):
+            eng._check(eng.lib.egx_logmel(eng._h, _ptr(self.audio), n, cfg.n_audio, cfg.spec_w, self._mode, self._preemph,
+                                          _ptr(self.spec), eng._stream()), "egx_logmel")
+            eng._check(eng.lib.egx_generator_forward(
+                eng._h, _ptr(self.spec), _ptr(self.prior), _ptr(self.sampled), n, *(_ptr(t) for t in self.out),
+                _ptr(self.ws), self.ws.numel(), eng._stream()), "egx_generator_forward")
+
+    def __call__(self, audio, prior, sampled_emotion=None):
+        if (self.sampled is None) != (sampled_emotion is None):
+            raise RuntimeError("this graph was captured %s sampled_emotion_feature" % ("without" if self.sampled is None else "with"))
+        self.audio.copy_(audio, non_blocking=True)
+        self.prior.copy_(prior, non_blocking=True)
+        if sampled_emotion is not None:
+            self.sampled.copy_(sampled_emotion, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -210,3 +210,20 @@ def test_full_size_batch_properties():
     with torch.no_grad():
         ref = og.generator_forward(sd, TED, spec[idx].cpu(), prior[idx].cpu())[0]
     assert rel_fro(poses[idx].cpu(), ref) <= TOL["tc"]
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_cuda_graph_replay_matches_eager(n):
+    """Engine.capture: one cudaGraphLaunch for log-mel + forward at a fixed small batch == the eager launches."""
+    eng, _ = _engine("ted", 0, "tc")
+    path = eng.capture(n)
+    for seed in (3, 4):
+        audio = torch.from_numpy(synth.synth_audio(n, TED.n_audio, seed=seed)).cuda()
+        prior = torch.from_numpy(synth.synth_prior(n, TED.prior_frames, TED.pose_dim, seed)).cuda()
+        eager = eng.generator_forward(eng.logmel(audio, LOGMEL_LOG_IN, True), prior)
+        got = path(audio, prior)
+        torch.cuda.synchronize()
+        for a, b in zip(got, eager):
+            assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="captured without"):
+        path(audio, prior, torch.zeros(n, TED.frames, TED.d_model, device="cuda"))
