@@ -36,7 +36,12 @@ S3_FLOP_PER_CLIP = 4.247e9           # trunk convolutions (layer1-3 + final conv
 STAGE_WORK = {                        # (bound, work per clip): bytes for hbm, flop for tensor
     "S1_frontend": ("hbm", 180_908.0),
     "S2_stem": ("hbm", 609_280.0),
-    "S3_trunk_conv": ("tensor", 4.247e9),
+    # trunk convolutions per layer (SURVEY.md §8(d) gives 991 / 1248 / 1963 + 45 MFLOP per clip).  Layers 2-3 are
+    # tensor-bound.  Layer 1 (32 channels) is HBM-bound: 5 map transfers of 128*70*32*2 B per block (conv1: x in,
+    # y1 out; conv2: y1 + residual in, block output out), 3 blocks, for 122 us of math at peak per conv
+    "S3_conv_layer1": ("hbm", 3 * 5 * 128 * 70 * 32 * 2.0),
+    "S3_conv_layer2": ("tensor", 1.248e9),
+    "S3_conv_layer3": ("tensor", 1.963e9 + 0.045e9),
     # S4 (SE gate * y + residual + ReLU) is fused into conv2's epilogue; what is left under this tag are the three
     # small launches per block that compute the gate ahead of conv2, so SURVEY.md §8(d) has S3+S4 reported jointly
     # against the tensor roofline (see "S3+S4_trunk" below) and S4 alone carries no roofline of its own
@@ -54,13 +59,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
-def conv_traffic_per_launch(B):
-    """dram__bytes_read.sum + dram__bytes_write.sum per trunk-convolution launch, from the committed ncu pass over one
-    step (profiles/r1_conv_dram.json, captured at `clips` clips and scaled linearly: every conv streams its maps once)."""
+def conv_traffic_per_launch(B, layer=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per trunk-convolution launch (of one layer, or of all), from the
+    committed ncu pass over one step (profiles/r1_conv_dram.json, captured at `clips` clips and scaled linearly:
+    every conv streams its maps once)."""
     p = os.path.join(ROOT, "profiles", "r1_conv_dram.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
+    if layer is not None:
+        d = dict(d.get("layers", {}).get(layer, {}), clips=d["clips"])
+        if "dram_bytes_per_launch" not in d:
+            return None
     return d["dram_bytes_per_launch"] * B / d["clips"]
 
 
@@ -300,28 +310,51 @@ def run_own_arm(args):
                     ach = work * B / (ms_per_step * 1e-3) / 1e12
                     ent.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["tf_sustained"])
             per_stage[nm] = ent
-        s3 = per_stage.get("S3_trunk_conv", {})
-        s4 = per_stage.get("S4_se", {})
-        if s3 and s4:
-            ms34 = s3["ms_per_step"] + s4["ms_per_step"]
-            ach = S3_FLOP_PER_CLIP * B / (ms34 * 1e-3) / 1e12
-            per_stage["S3+S4_trunk"] = {"ms_per_step": ms34, "launches_per_step": s3["launches_per_step"] + s4["launches_per_step"],
-                                        "bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
-        n_conv = max(1.0, s3.get("launches_per_step", 1.0))
-        roofline = {
-            "bound": "tensor", "kernel": "trunk 3x3 convolutions (S3, %d launches per step)" % n_conv,
-            "achieved": s3.get("achieved"), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": s3.get("frac"), "traffic": conv_traffic_per_launch(B),
-            "peak_source": peaks["src"] + " (sustained bf16/fp16 dense, kernel timed inside a long step)",
-            "flop_per_launch": S3_FLOP_PER_CLIP * B / n_conv,
-            "ms_per_launch": s3.get("ms_per_step", 0.0) / n_conv,
-        }
+        # all trunk convolutions together against the tensor roofline, alone and with what
+        # is left of S4 (the SE gate ahead of conv2; its gate*y + residual pass is fused into conv2's epilogue)
+        layers = {k: v for k, v in per_stage.items() if k.startswith("S3_conv_layer")}
+        if layers:
+            ms3 = sum(v["ms_per_step"] for v in layers.values())
+            n3 = sum(v["launches_per_step"] for v in layers.values())
+            ach = S3_FLOP_PER_CLIP * B / (ms3 * 1e-3) / 1e12
+            per_stage["S3_trunk_conv"] = {"ms_per_step": ms3, "launches_per_step": n3, "bound": "tensor", "achieved": ach,
+                                          "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
+            s4 = per_stage.get("S4_se")
+            if s4:
+                ms34 = ms3 + s4["ms_per_step"]
+                ach = S3_FLOP_PER_CLIP * B / (ms34 * 1e-3) / 1e12
+                per_stage["S3+S4_trunk"] = {"ms_per_step": ms34, "launches_per_step": n3 + s4["launches_per_step"],
+                                            "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+                                            "frac": ach / peaks["tf_sustained"]}
+        # roofline of the dominant kernel family: the trunk layer with the largest share of the step, against the
+        # roofline that bounds it (layer 1: HBM; layers 2-3: tensor pipe)
+        dom = max(layers, key=lambda k: layers[k]["ms_per_step"]) if layers else None
+        roofline = None
+        if dom:
+            st = layers[dom]
+            n_l = max(1.0, st["launches_per_step"])
+            bound, work = STAGE_WORK[dom]
+            lay = dom.replace("S3_conv_", "")
+            roofline = {
+                "bound": bound,
+                "kernel": "trunk convolutions of %s (%d launches per step: %s)" % (
+                    lay, n_l, {"layer1": "conv_tc_kernel<32,32> SE-sum and gated-residual flavours",
+                               "layer2": "conv_tc_kernel<64,64> + the stride-2 / 1x1 convs of its first block",
+                               "layer3": "conv128_tc_kernel + the stride-2 / 1x1 convs of its first block + final conv"}.get(lay, lay)),
+                "achieved": st["achieved"], "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["tf_sustained"],
+                "unit": st["unit"], "frac": st["frac"], "traffic": conv_traffic_per_launch(B, lay),
+                "peak_source": peaks["src"] + (" (copy bandwidth)" if bound == "hbm" else
+                                               " (sustained bf16/fp16 dense, kernel timed inside a long step)"),
+                ("bytes_per_launch" if bound == "hbm" else "flop_per_launch"): work * B / n_l,
+                "ms_per_launch": st["ms_per_step"] / n_l,
+                "all_trunk_convs_vs_tensor_peak": per_stage.get("S3_trunk_conv", {}).get("frac"),
+            }
         cpu_val, cpu_ms, cores = (None, None, os.cpu_count())
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_val, cpu_ms, cores = time_cpu(args.cpu_clips, 3, 1)
+            cpu_val, cpu_ms, cores = time_cpu(args.cpu_clips, 24, 2)
             cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_clips} TED clips x 3 steps (oracle port: log-mel fp64 numpy + "
+                   "sample": f"{args.cpu_clips} TED clips x 24 steps (oracle port: log-mel fp64 numpy + "
                              f"generator fp32 torch, {cores} threads)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -349,7 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--clips-per-gpu", type=int, default=4096)
-    ap.add_argument("--cpu-clips", type=int, default=32)
+    ap.add_argument("--cpu-clips", type=int, default=32)   # the CPU path is fastest per clip around this batch
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=1024)

@@ -653,6 +653,7 @@ int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& bl
         for (int b = 0; b < nblk[li]; ++b, ++bi) {
             const BlockW& bw = blocks[bi];
             const __half* res = x;
+            const int conv_stage = li == 0 ? 3 : 8 + li;      // 3 | 9 | 10 | 11: trunk convolutions of layer li + 1
             if (se_fused()) {
                 // SE gate ahead of conv2 (k_trunk.cu K4c/K4d): conv1 sums its output per tile, the window means go
                 // through conv2's own weights as a [B x 9C] x [9C x C] GEMM, and conv2's epilogue applies
@@ -660,7 +661,7 @@ int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& bl
                 const int C = bw.conv2.cout;
                 if (C > kSeMaxC || bw.conv2.cin != C || bw.conv2.ks != 3 || bw.conv2.stride != 1) EGX_FAIL(h, "unsupported SE block geometry");
                 {
-                    StageScope sc(h, 3);
+                    StageScope sc(h, conv_stage);
                     LAUNCH(h, launch_conv_tc(bw.conv1, x, B, Hc, Wc, y, 0, tb.se_sums, s));
                     if (bw.has_down) {
                         LAUNCH(h, launch_conv_tc(bw.down, x, B, Hc, Wc, tb.down, 0, nullptr, s));
@@ -674,7 +675,7 @@ int run_trunk_tc(egx_handle* h, const ConvW& stem, const std::vector<BlockW>& bl
                     LAUNCH(h, launch_gemm_tc(tb.se_win, 9 * C, bw.conv2.w16, 9 * C, B, C, 9 * C, GemmEpi{}, tb.se_mean, C, nullptr, 0, s));
                     LAUNCH(h, launch_se_gate(bw.se, bw.conv2, tb.se_mean, B, tb.se_gate, s));
                 }
-                StageScope sc(h, 3);
+                StageScope sc(h, conv_stage);
                 LAUNCH(h, launch_conv_tc(bw.conv2, y, B, Ho, Wo, z, 0, nullptr, s, tb.se_gate, res));
                 // rotate: the block's output z becomes x; the old x (the residual) is free again
                 __half* t = x; x = z; z = t;
@@ -723,7 +724,7 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
     __half* t3 = nullptr;
     if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;
     {
-        StageScope sc(h, 3);
+        StageScope sc(h, 10);
         LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, nullptr, s));
     }
     StageScope sc5(h, 5);

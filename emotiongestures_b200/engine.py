@@ -75,9 +75,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.egx_launch_count(self._h))
 
-    N_STAGES = 9
-    STAGE_NAMES = ("other", "S1_frontend", "S2_stem", "S3_trunk_conv", "S4_se", "S5_proj_gemm",
-                   "S6_enc_dec", "S7", "S8_fgd")
+    N_STAGES = 12
+    STAGE_NAMES = ("other", "S1_frontend", "S2_stem", "S3_conv_layer1", "S4_se", "S5_proj_gemm",
+                   "S6_enc_dec", "S7", "S8_fgd", "S3_conv_layer2", "S3_conv_layer3", "S3_conv_layer4")
 
     def profile_enable(self, max_launches: int):
         self._check(self.lib.egx_profile_enable(self._h, int(max_launches)), "egx_profile_enable")

@@ -186,7 +186,8 @@ EGX_API int  egx_debug_attention_tc(egx_handle* h, const void* q16, int ldq, int
 
 /* Measurement hooks (bench.py): with profiling enabled (max_launches > 0) every kernel launch is
  * bracketed by a CUDA-event pair on the launching stream, tagged with its stage of SURVEY.md
- * §8(d) (1 front-end, 2 stem, 3 trunk convolutions, 4 SE gate/apply, 5 projection GEMMs,
+ * §8(d) (1 front-end, 2 stem, 3 trunk convolutions of layer 1 — on the tensor-core arm 9 / 10 / 11 are those of
+ * layers 2 / 3 (+ final conv) / 4, on the fp32 arm 3 covers all —, 4 SE gate, 5 projection GEMMs,
  * 6 encoder+decoder, 8 FGD statistics, 0 other).  egx_profile_read waits for the recorded
  * events, sums elapsed milliseconds and launch counts per stage and resets the recording. */
 EGX_API int  egx_profile_enable(egx_handle* h, int max_launches);
