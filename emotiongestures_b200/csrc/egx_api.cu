@@ -710,27 +710,22 @@ int run_trunk_tc(egx_handle* h, const float* spec, int B, TcSlots& sl, int upto,
     return run_trunk_tc(h, h->w.stem, h->w.blocks, 3, h->H[0], h->W[0], spec, B, tb, upto, result, &Ho, &Wo, s);
 }
 
-int forward_tc(egx_handle* h, const float* spec, const float* prior, const float* sampled, int B, float* poses,
-               float* emo_feat, float* sem_feat, float* logits, void* ws, size_t ws_bytes, cudaStream_t s) {
+// Transformer tail of the tensor-core arm for `B` clips whose rows start at r0 of the full-batch taps: encoder-tail
+// Linear chain, projections, classifier header, fusion, encoder, decoder, pose head (Full_model/Models.py:124-130,
+// 199-212, 237-293, 411-425).  Chunk-local intermediates live in the first rows of the full-size buffers of `sl`.
+int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const __half* pconv16, const float* sampled,
+                    float* poses, float* emo_feat, float* sem_feat, float* logits, size_t r0, cudaStream_t s) {
     const egx_cfg& c = h->cfg;
-    Plan p;
-    p.base = static_cast<char*>(ws);
-    TcSlots sl = plan_tc(h, B, p);
-    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
     const Weights& w = h->w;
     const int R = B * c.frames, d = c.d_model, F = c.frames, P = c.pose_dim, P8 = sl.P8;
     const int hk = c.n_head * c.d_k, HW3 = h->H[2] * h->W[2];
-
-    __half* t3 = nullptr;
-    if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;
-    {
-        StageScope sc(h, 10);
-        LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, nullptr, s));
-    }
+    float* spec_feat = sl.spec_feat + r0 * d;       // taps keep the whole batch
+    float* prior_feat = sl.prior_feat + r0 * d;
+    float* enc_out = sl.enc_out + r0 * d;
+    float* dec_out = sl.dec_out + r0 * d;
     StageScope sc5(h, 5);
-    if (linear_tc(h, w.a_fc, sl.fcin, HW3, R, sl.spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
-    if (run_prior_front<__half>(h, prior, B, sl.mem, sl.pconv16, P8, s)) return 1;
-    if (linear_tc(h, w.p_fc, sl.pconv16, P8, R, sl.prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.a_fc, fcin, HW3, R, spec_feat, d, sl.spec16, d, 0, nullptr, 0, s)) return 1;
+    if (linear_tc(h, w.p_fc, pconv16, P8, R, prior_feat, d, sl.prior16, d, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.emo, sl.spec16, d, R, emo_feat, d, sl.emo16, d, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.sem, sl.spec16, d, R, sem_feat, d, nullptr, 0, 0, nullptr, 0, s)) return 1;
     if (linear_tc(h, w.hdr[0], sl.emo16, F * d, B, nullptr, 0, sl.h0, d, 1, nullptr, 0, s)) return 1;
@@ -753,9 +748,9 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
         if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, last ? sl.enc_out : x32, last ? sl.enc16 : sl.x16, s));
+        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, last ? enc_out : x32, last ? sl.enc16 : sl.x16, s));
     }
-    const float* dx32 = sl.prior_feat;
+    const float* dx32 = prior_feat;
     const __half* dx16 = sl.prior16;
     for (int l = 0; l < c.n_layers; ++l) {
         const MHAW& a = w.dec_attn[l];
@@ -769,13 +764,62 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
         LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
         if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
-        float* o32 = last ? sl.dec_out : x32;
+        float* o32 = last ? dec_out : x32;
         __half* o16 = last ? sl.dec16 : sl.x16;
         LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, o32, o16, s));
         dx32 = o32; dx16 = o16;
     }
     StageScope sc5b(h, 5);
     if (linear_tc(h, w.post_all, sl.dec16, d, R, poses, P, nullptr, 0, 0, nullptr, 0, s)) return 1;
+    return 0;
+}
+
+// clips per chunk of the transformer tail: a multiple of 6 (3 TED / 2 BEAT clips share an attention tile)
+int tail_chunk_clips() {
+    static const int n = [] {
+        const char* e = getenv("EGX_TAIL_CHUNK");
+        const int v = e ? atoi(e) : 0;
+        return v <= 0 ? (1 << 30) / 6 * 6 : std::max(6, v / 6 * 6);
+    }();
+    return n;
+}
+
+int forward_tc(egx_handle* h, const float* spec, const float* prior, const float* sampled, int B, float* poses,
+               float* emo_feat, float* sem_feat, float* logits, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const egx_cfg& c = h->cfg;
+    Plan p;
+    p.base = static_cast<char*>(ws);
+    TcSlots sl = plan_tc(h, B, p);
+    if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
+    const Weights& w = h->w;
+    const int R = B * c.frames, d = c.d_model, F = c.frames, P = c.pose_dim, P8 = sl.P8;
+    const int hk = c.n_head * c.d_k, HW3 = h->H[2] * h->W[2];
+
+    __half* t3 = nullptr;
+    if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;
+    {
+        StageScope sc(h, 10);
+        LAUNCH(h, launch_conv_tc(w.final_conv, t3, B, h->H[2], h->W[2], sl.fcin, 1, nullptr, s));
+    }
+    {
+        StageScope sc5(h, 5);
+        // the prior front runs on the whole batch: the memory variant's temporal memory sums over it
+        if (run_prior_front<__half>(h, prior, B, sl.mem, sl.pconv16, P8, s)) return 1;
+    }
+    // Everything after the trunk can run in chunks of clips (EGX_TAIL_CHUNK, off by default).  The idea: its GEMMs are
+    // bound by the bytes they write (QKV 428 MB, FFN hidden 285 MB per layer at B = 4096, both larger than the 126 MB
+    // L2) and every such tensor is read back by the next kernel, so chunk-sized tensors would stay in L2.  Measured:
+    // 34.9 ms/step unchunked, 35.2 at 1536 clips, 36.5 at 768 — the smaller launches lose more (tile quantisation,
+    // fixed prologue per launch) than L2 residency returns — so one pass over the whole batch stays the default.
+    // Per-clip results do not depend on the chunking (rows are independent, attention groups stay aligned).
+    const int chunk = tail_chunk_clips();
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        const size_t r0 = (size_t)b0 * F;
+        if (forward_tail_tc(h, sl, nb, sl.fcin + r0 * HW3, sl.pconv16 + r0 * P8, sampled ? sampled + r0 * d : nullptr,
+                            poses + r0 * P, emo_feat + r0 * d, sem_feat + r0 * d, logits + (size_t)b0 * 8, r0, s))
+            return 1;
+    }
     return 0;
 }
 

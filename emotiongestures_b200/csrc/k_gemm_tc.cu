@@ -37,10 +37,22 @@ struct GemmCfg {
     static constexpr int kABytes = GM * GK * 2;
     static constexpr int kBBytes = BN * GK * 2;
     static constexpr int kStageBytes = RES ? kABytes : kABytes + kBBytes;
-    static constexpr int kStages = RES ? 4 : (BN == 256 ? 4 : 6);
-    static constexpr int kRingBytes = kStages * kStageBytes;
-    // layout: [resident B: num_kb * kBBytes (RES only)] [ring] [barriers]
-    static constexpr int total(int num_kb) { return (RES ? num_kb * kBBytes : 0) + kRingBytes + 256 + 1024; }
+    static constexpr int kMaxStages = 8;
+    // ring depth: everything the 227 KB leave after the resident slice / store staging, at most 8 stages.  The TMA
+    // round trip is ~3000 cycles under load and a 128 x 256 x 64 k-block is 512 cycles of MMA, so four stages starve
+    // the tensor pipe (measured: the QKV projection at 3.5x its MMA time)
+    static constexpr int stages(int num_kb, bool tma_store) {
+        const int room = 227 * 1024 - (RES ? num_kb * kBBytes : 0) - (tma_store ? kStoreBytes : 0) - 256 - 1024;
+        const int n = room / kStageBytes;
+        return n > kMaxStages ? kMaxStages : n;
+    }
+    // fp16 output staging for TMA stores: [group 2][buffer 2] slabs of 128 rows x 32 columns (64-byte rows, SWIZZLE_64B)
+    static constexpr int kSlabBytes = GM * 64;
+    static constexpr int kStoreBytes = 4 * kSlabBytes;
+    // layout: [resident B: num_kb * kBBytes (RES only)] [ring] [store staging (optional)] [barriers 256 B]
+    static constexpr int total(int num_kb, bool tma_store) {
+        return (RES ? num_kb * kBBytes : 0) + stages(num_kb, tma_store) * kStageBytes + 256 + (tma_store ? kStoreBytes : 0) + 1024;
+    }
     static constexpr uint32_t kTmemCols = 2 * BN;
 };
 
@@ -78,20 +90,25 @@ struct GemmTcEpi {
     int relu;
     float* out32; int ld32;
     __half* out16; int ld16;
+    int tma16;        // fp16 output through shared-memory slabs + TMA stores (tmC) instead of per-thread stores
 };
+
+__device__ __forceinline__ void gemm_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int BN, bool RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int K, GemmTcEpi ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmTcEpi ep) {
     using S = GemmCfg<BN, RES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int num_kb = (K + GK - 1) / GK;
     unsigned char* ring = smem + (RES ? num_kb * S::kBBytes : 0);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + S::kRingBytes);
-    uint64_t* empty = full + S::kStages;
-    uint64_t* tmem_full = empty + S::kStages;      // [2]
+    const int n_stages = S::stages(num_kb, ep.tma16 != 0);
+    unsigned char* store_stage = ring + n_stages * S::kStageBytes; // 1024-byte aligned: swizzle atoms of the slabs
+    uint64_t* full = reinterpret_cast<uint64_t*>(store_stage + (ep.tma16 ? S::kStoreBytes : 0));
+    uint64_t* empty = full + S::kMaxStages;
+    uint64_t* tmem_full = empty + S::kMaxStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* b_full = tmem_empty + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
@@ -102,7 +119,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        for (int i = 0; i < S::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        if (ep.tma16) prefetch_tmap(&tmC);
+        for (int i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(b_full, 1);
         fence_barrier_init();
@@ -119,13 +137,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_expect_tx(b_full, (uint32_t)num_kb * S::kBBytes);
                 for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem + kb * S::kBBytes, &tmB, b_full, kb * GK, walk.n0);
             }
-            uint32_t it = 0;
+            int st = 0;
+            uint32_t ph = 0;                             // ring slot and its phase parity
             for (int i = 0; i < walk.count; ++i) {
                 int m0, n0;
                 gemm_tile<BN, RES>(walk, i, &m0, &n0);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int st = it % S::kStages;
-                    mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
+                for (int kb = 0; kb < num_kb; ++kb, st = st + 1 == n_stages ? 0 : st + 1, ph ^= (st == 0)) {
+                    mbar_wait(&empty[st], ph ^ 1);
                     unsigned char* a = ring + st * S::kStageBytes;
                     mbar_expect_tx(&full[st], S::kStageBytes);
                     tma_load_2d(a, &tmA, &full[st], kb * GK, m0);
@@ -137,7 +155,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(GM, BN);
             constexpr uint32_t kDescHi = smem_desc_hi<128>();
-            uint32_t it = 0;
+            int st = 0;
+            uint32_t ph = 0;
             const uint32_t res_lo = smem_desc_lo(smem_u32(smem));
             if (RES && walk.count > 0) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (uint32_t tcount = 0; (int)tcount < walk.count; ++tcount) {
@@ -145,9 +164,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int st = it % S::kStages;
-                    mbar_wait(&full[st], (it / S::kStages) & 1);
+                for (int kb = 0; kb < num_kb; ++kb, st = st + 1 == n_stages ? 0 : st + 1, ph ^= (st == 0)) {
+                    mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * S::kStageBytes));
                     const uint32_t b_lo = RES ? res_lo + ((kb * S::kBBytes) >> 4) : a_lo + (S::kABytes >> 4);
@@ -169,24 +187,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = q * 32 + lane;
         const bool relu = ep.relu != 0;
         const bool add_vec = (ep.addend_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.addend) & 15) == 0;
+        // TMA-store path: this thread's row of the group's slabs, 16-byte chunks XOR-swizzled like SWIZZLE_64B
+        const uint32_t slab_u32 = smem_u32(store_stage) + grp * 2 * S::kSlabBytes;
+        const uint32_t slab_row = row * 64, slab_swz = (row >> 1) & 3;
+        uint32_t n_slab = 0;                                  // slabs this group has handed to TMA so far
         for (uint32_t tcount = grp; (int)tcount < walk.count; tcount += 2) {
             int m0, n0;
             gemm_tile<BN, RES>(walk, (int)tcount, &m0, &n0);
             const int m = m0 + row;
-            mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
-            tc_fence_after();
             const float* add_row = nullptr;
             if (ep.addend && m < M)
                 add_row = ep.addend + (size_t)(ep.addend_rows ? m % ep.addend_rows : m) * ep.addend_ld;
+            // the residual / positional addend is the only global read of the epilogue (128 B per thread and chunk,
+            // every thread in its own row): it is requested one chunk ahead, the first one before the accumulator wait
+            const bool add_pre = add_row != nullptr && add_vec;
+            float4 ad_n[8];
+            if (add_pre && n0 + 32 <= N) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + n0) + j4);
+            }
+            mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;                       // warp-uniform
                 float v[32];
+                float4 ad_c[8];
+                if (add_pre) {                               // uniform per thread for the whole tile
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) ad_c[j4] = ad_n[j4];
+                    if (c + 1 < BN / 32 && nb + 64 <= N) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + nb + 32) + j4);
+                    }
+                }
                 __syncwarp();
                 tmem_ld32(taddr + c * 32, v);
-                if (m < M) {
+                if (ep.tma16) {
+                    // the slab this chunk goes to was handed to TMA two chunks ago: its reads must be over
+                    if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    gemm_named_bar(1 + grp, 128);
+                }
+                if (m < M || ep.tma16) {
                     const bool full_chunk = nb + 32 <= N;
                     if (full_chunk) {
 #pragma unroll
@@ -194,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 bi = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (add_row) {
-                                if (add_vec) ad = __ldg(reinterpret_cast<const float4*>(add_row + nb) + j4);
+                                if (add_vec) ad = ad_c[j4];
                                 else ad = make_float4(__ldg(add_row + nb + 4 * j4), __ldg(add_row + nb + 4 * j4 + 1),
                                                       __ldg(add_row + nb + 4 * j4 + 2), __ldg(add_row + nb + 4 * j4 + 3));
                             }
@@ -219,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[j] = t;
                         }
                     }
-                    if (ep.out32) {
+                    if (ep.out32 && m < M) {
                         float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
                         if (full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0) {
                             // 256-bit stores: every instruction writes whole 32-byte sectors
@@ -234,13 +278,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 8; ++j)
                                 reinterpret_cast<float4*>(o)[j] =
                                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else if ((ep.ld32 & 1) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 7) == 0) {
+                            // odd widths such as the 126-wide pose rows: 8-byte stores
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (nb + 2 * j + 1 < N) reinterpret_cast<float2*>(o)[j] = make_float2(v[2 * j], v[2 * j + 1]);
+                                else if (nb + 2 * j < N) o[2 * j] = v[2 * j];
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (nb + j < N) o[j] = v[j];
                         }
                     }
-                    if (ep.out16) {
+                    if (ep.tma16) {
+                        const uint32_t dst = slab_u32 + (n_slab & 1) * S::kSlabBytes + slab_row;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t u[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 h2 = __floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                                u[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ slab_swz) << 4)),
+                                         "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+                        }
+                    } else if (ep.out16 && m < M) {
                         __half* o = ep.out16 + (size_t)m * ep.ld16 + nb;
                         if (full_chunk && (ep.ld16 & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out16) & 31) == 0) {
 #pragma unroll
@@ -272,11 +336,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if (ep.tma16) {
+                    // generic-proxy writes -> visible to the TMA engine, then one thread hands the slab over;
+                    // rows >= M and columns >= N are clipped by the tensor map
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    gemm_named_bar(1 + grp, 128);
+                    if (row == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&tmC)),
+                                     "r"(slab_u32 + (n_slab & 1) * S::kSlabBytes), "r"(nb), "r"(m0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++n_slab;
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[grp]);
         }
+        if (ep.tma16 && row == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -294,12 +373,14 @@ __global__ void cvt_pad_kernel(const float* __restrict__ in, int64_t rows, int c
 }
 
 int g_gemm_sms = 0;
+int g_gemm_tma_store = 0;   // EGX_GEMM_TMA_STORE=1: fp16 outputs through shared-memory slabs + TMA stores (measured: no gain over the
+                            // per-thread 256-bit stores, and the slabs cost two ring stages)
 int g_gemm_res = 1;      // EGX_GEMM_RES=0 (attribution experiments only): never keep the weight slice resident
 
 template <int BN, bool RES>
 int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmTcEpi& ep,
               cudaStream_t s) {
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc_;
     const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, dB[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t sA[1] = {(uint64_t)lda * 2}, sB[1] = {(uint64_t)ldw * 2};
     const uint32_t bA[2] = {GK, GM}, bB[2] = {GK, BN};
@@ -308,7 +389,19 @@ int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, 
     const int n_tiles = (N + BN - 1) / BN, tiles = ((M + GM - 1) / GM) * n_tiles;
     int grid = tiles < g_gemm_sms ? tiles : g_gemm_sms;
     if (RES) grid = grid / n_tiles * n_tiles;          // every CTA keeps one n-slice
-    gemm_tc_kernel<BN, RES><<<grid, kGemmThreads, GemmCfg<BN, RES>::total((K + GK - 1) / GK), s>>>(ta, tb, M, N, K, ep);
+    // fp16 output through TMA stores when the pitch allows a tensor map and the staging slabs still fit
+    GemmTcEpi e2 = ep;
+    const int num_kb = (K + GK - 1) / GK;
+    e2.tma16 = g_gemm_tma_store && ep.out16 && (ep.ld16 % 8) == 0 && (reinterpret_cast<uintptr_t>(ep.out16) & 15) == 0 &&
+               GemmCfg<BN, RES>::stages(num_kb, true) >= 3;
+    if (GemmCfg<BN, RES>::stages(num_kb, e2.tma16 != 0) < 2) return -1;
+    tc_ = ta;
+    if (e2.tma16) {
+        const uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[1] = {(uint64_t)ep.ld16 * 2};
+        const uint32_t bC[2] = {32, GM};
+        if (!make_tmap_f16(&tc_, ep.out16, 2, dC, sC, bC, nullptr, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+    }
+    gemm_tc_kernel<BN, RES><<<grid, kGemmThreads, GemmCfg<BN, RES>::total(num_kb, e2.tma16 != 0), s>>>(ta, tb, tc_, M, N, K, e2);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -320,11 +413,10 @@ int gemm_tc_init_device() {
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     if (const char* e = getenv("EGX_GEMM_RES")) g_gemm_res = atoi(e);
-    const int res_max = kResMaxBytes + GemmCfg<128, true>::total(0);
-    if (cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<128, false>::total(0)) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             GemmCfg<256, false>::total(0)) != cudaSuccess) return -1;
+    if (const char* e = getenv("EGX_GEMM_TMA_STORE")) g_gemm_tma_store = atoi(e);
+    const int res_max = 227 * 1024;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     return 0;
@@ -341,7 +433,7 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 // A: [M][K] fp16 with row pitch lda (elements, multiple of 8); W: [N][K] fp16 with row pitch ldw.
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
-    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16};
+    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16, 0};
     const int num_kb = (K + GK - 1) / GK;
     const int m_tiles = (M + GM - 1) / GM;
     // weights resident when the slice fits and every CTA gets several m-tiles to amortise loading it
