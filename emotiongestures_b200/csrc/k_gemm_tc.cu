@@ -90,6 +90,7 @@ struct GemmTcEpi {
     int relu;
     float* out32; int ld32;
     __half* out16; int ld16;
+    int debug;        // EGX_GEMM_DEBUG (attribution experiments only, wrong results): 1 = no global stores, 2 = no epilogue
     int tma16;        // fp16 output through shared-memory slabs + TMA stores (tmC) instead of per-thread stores
 };
 
@@ -209,22 +210,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(q * 32) << 16);
+            // accumulator chunks are read one ahead: the TMEM load of chunk c + 1 is in flight while chunk c is
+            // converted and stored (with the load and its wait back to back the epilogue, not the MMA, set the pace)
+            uint32_t rn[32];
+            __syncwarp();
+            if (n0 < N && !(ep.debug & 2)) tmem_ld32_issue(taddr, rn);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;                       // warp-uniform
+                if (ep.debug & 2) break;
                 float v[32];
-                float4 ad_c[8];
-                if (add_pre) {                               // uniform per thread for the whole tile
+                tmem_ld_wait32(rn);
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) ad_c[j4] = ad_n[j4];
-                    if (c + 1 < BN / 32 && nb + 64 <= N) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + nb + 32) + j4);
-                    }
-                }
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
                 __syncwarp();
-                tmem_ld32(taddr + c * 32, v);
+                if (c + 1 < BN / 32 && nb + 32 < N) tmem_ld32_issue(taddr + (c + 1) * 32, rn);
+
                 if (ep.tma16) {
                     // the slab this chunk goes to was handed to TMA two chunks ago: its reads must be over
                     if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -238,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 bi = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (add_row) {
-                                if (add_vec) ad = ad_c[j4];
+                                if (add_vec) ad = ad_n[j4];
                                 else ad = make_float4(__ldg(add_row + nb + 4 * j4), __ldg(add_row + nb + 4 * j4 + 1),
                                                       __ldg(add_row + nb + 4 * j4 + 2), __ldg(add_row + nb + 4 * j4 + 3));
                             }
@@ -263,6 +265,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[j] = t;
                         }
                     }
+                    if (add_pre && c + 1 < BN / 32 && nb + 64 <= N) {      // next chunk's addend: in flight during the stores
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + nb + 32) + j4);
+                    }
+                    if (ep.debug & 1) continue;
                     if (ep.out32 && m < M) {
                         float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
                         if (full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0) {
@@ -375,6 +382,7 @@ __global__ void cvt_pad_kernel(const float* __restrict__ in, int64_t rows, int c
 int g_gemm_sms = 0;
 int g_gemm_tma_store = 0;   // EGX_GEMM_TMA_STORE=1: fp16 outputs through shared-memory slabs + TMA stores (measured: no gain over the
                             // per-thread 256-bit stores, and the slabs cost two ring stages)
+int g_gemm_debug = 0;
 int g_gemm_res = 1;      // EGX_GEMM_RES=0 (attribution experiments only): never keep the weight slice resident
 
 template <int BN, bool RES>
@@ -414,6 +422,7 @@ int gemm_tc_init_device() {
     if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     if (const char* e = getenv("EGX_GEMM_RES")) g_gemm_res = atoi(e);
     if (const char* e = getenv("EGX_GEMM_TMA_STORE")) g_gemm_tma_store = atoi(e);
+    if (const char* e = getenv("EGX_GEMM_DEBUG")) g_gemm_debug = atoi(e);
     const int res_max = 227 * 1024;
     if (cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
@@ -433,7 +442,7 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 // A: [M][K] fp16 with row pitch lda (elements, multiple of 8); W: [N][K] fp16 with row pitch ldw.
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
-    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16, 0};
+    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16, g_gemm_debug, 0};
     const int num_kb = (K + GK - 1) / GK;
     const int m_tiles = (M + GM - 1) / GM;
     // weights resident when the slice fits and every CTA gets several m-tiles to amortise loading it
