@@ -210,22 +210,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(q * 32) << 16);
-            // accumulator chunks are read one ahead: the TMEM load of chunk c + 1 is in flight while chunk c is
-            // converted and stored (with the load and its wait back to back the epilogue, not the MMA, set the pace)
-            uint32_t rn[32];
-            __syncwarp();
-            if (n0 < N && !(ep.debug & 2)) tmem_ld32_issue(taddr, rn);
+            // (issuing the TMEM load of chunk c + 1 before chunk c is converted was measured: no gain, and the register
+            // copies it needs cost issue slots — this epilogue is instruction-issue bound)
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int nb = n0 + c * 32;
                 if (nb >= N) break;                       // warp-uniform
                 if (ep.debug & 2) break;
                 float v[32];
-                tmem_ld_wait32(rn);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
                 __syncwarp();
-                if (c + 1 < BN / 32 && nb + 32 < N) tmem_ld32_issue(taddr + (c + 1) * 32, rn);
+                tmem_ld32(taddr + c * 32, v);
 
                 if (ep.tma16) {
                     // the slab this chunk goes to was handed to TMA two chunks ago: its reads must be over
@@ -235,21 +229,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (m < M || ep.tma16) {
                     const bool full_chunk = nb + 32 <= N;
                     if (full_chunk) {
+                        // bias / ReLU / addend are uniform per launch: a Linear without them (the attention projections)
+                        // pays for none of the 64 adds — the epilogue is instruction-issue bound
+                        if (ep.bias) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 bi = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (add_row) {
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 bi = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j4);
+                                v[4 * j4] += bi.x; v[4 * j4 + 1] += bi.y; v[4 * j4 + 2] += bi.z; v[4 * j4 + 3] += bi.w;
+                            }
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (add_row) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                float4 ad;
                                 if (add_vec) ad = ad_n[j4];
                                 else ad = make_float4(__ldg(add_row + nb + 4 * j4), __ldg(add_row + nb + 4 * j4 + 1),
                                                       __ldg(add_row + nb + 4 * j4 + 2), __ldg(add_row + nb + 4 * j4 + 3));
-                            }
-                            const float bv[4] = {bi.x, bi.y, bi.z, bi.w}, av[4] = {ad.x, ad.y, ad.z, ad.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float t = v[4 * j4 + e] + bv[e];
-                                if (relu) t = fmaxf(t, 0.f);
-                                v[4 * j4 + e] = t + av[e];
+                                v[4 * j4] += ad.x; v[4 * j4 + 1] += ad.y; v[4 * j4 + 2] += ad.z; v[4 * j4 + 3] += ad.w;
                             }
                         }
                     } else {
