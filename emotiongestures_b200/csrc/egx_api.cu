@@ -238,12 +238,27 @@ bool build_logmel_tables(egx_handle* h) {
         for (int k = first; k <= last; ++k) wts.push_back((float)row[k]);
         ptr[m + 1] = (int)wts.size();
     }
+    // per-pass twiddles of the radix-8 Stockham FFT laid out [pass][t][j] (pass 0: Ns = 8, pass 1: Ns = 64), so that the
+    // 32 lanes j of a warp read consecutive entries: tw_pass[pass][t][j] = W512^((j mod Ns) * t * 64 / Ns)
+    std::vector<float2> tw_pass(2 * 8 * 64);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ns = pass ? 64 : 8;
+        for (int t = 0; t < 8; ++t)
+            for (int j = 0; j < 64; ++j) tw_pass[(pass * 8 + t) * 64 + j] = tw512[((j & (ns - 1)) * t * (64 / ns)) & 511];
+    }
+    // mel weights in ELL layout [tap][mel] (zero padded): lanes = mels read consecutive floats
+    int max_taps = 0;
+    std::vector<int> cnt(n_mels + 1, 0);
+    for (int m = 0; m < n_mels; ++m) { cnt[m] = ptr[m + 1] - ptr[m]; max_taps = std::max(max_taps, cnt[m]); }
+    std::vector<float> ell((size_t)max_taps * n_mels, 0.f);
+    for (int m = 0; m < n_mels; ++m)
+        for (int p = 0; p < cnt[m]; ++p) ell[(size_t)p * n_mels + m] = wts[ptr[m] + p];
     h->lm.window = upload(h, window);
-    h->lm.tw512 = upload(h, tw512);
+    h->lm.tw512 = upload(h, tw_pass);
     h->lm.tw1024 = upload(h, tw1024);
     h->lm.mel_start = upload(h, start);
-    h->lm.mel_ptr = upload(h, ptr);
-    h->lm.mel_w = upload(h, wts);
+    h->lm.mel_ptr = upload(h, cnt);
+    h->lm.mel_w = upload(h, ell);
     return h->lm.window && h->lm.tw512 && h->lm.tw1024 && h->lm.mel_start && h->lm.mel_ptr && h->lm.mel_w;
 }
 
@@ -792,8 +807,8 @@ int forward_tc(egx_handle* h, const float* spec, const float* prior, const float
     TcSlots sl = plan_tc(h, B, p);
     if (p.off > ws_bytes) EGX_FAIL(h, "workspace too small: need " + std::to_string(p.off));
     const Weights& w = h->w;
-    const int R = B * c.frames, d = c.d_model, F = c.frames, P = c.pose_dim, P8 = sl.P8;
-    const int hk = c.n_head * c.d_k, HW3 = h->H[2] * h->W[2];
+    const int d = c.d_model, F = c.frames, P = c.pose_dim, P8 = sl.P8;
+    const int HW3 = h->H[2] * h->W[2];
 
     __half* t3 = nullptr;
     if (run_trunk_tc(h, spec, B, sl, 3, &t3, s)) return 1;

@@ -154,11 +154,11 @@ struct SkeletonW {
 // Log-mel tables (built in float64 on the host, stored as float32)
 struct LogmelTables {
     float* window = nullptr;      // [1024] periodic Hann
-    float2* tw512 = nullptr;      // [256] exp(-2*pi*i*k/512)
+    float2* tw512 = nullptr;      // [2][8][64] per-pass twiddles of the radix-8 FFT, W512^((j mod Ns) * t * 64 / Ns)
     float2* tw1024 = nullptr;     // [513] exp(-2*pi*i*k/1024)
     int* mel_start = nullptr;     // [128] first bin with non-zero weight
-    int* mel_ptr = nullptr;       // [129] CSR offsets into mel_w
-    float* mel_w = nullptr;       // packed non-zero weights
+    int* mel_ptr = nullptr;       // [129] number of taps of every mel filter
+    float* mel_w = nullptr;       // [taps][128] non-zero weights, tap-major (zero padded)
 };
 
 }  // namespace egx

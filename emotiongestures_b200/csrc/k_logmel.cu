@@ -69,11 +69,12 @@ __device__ __forceinline__ void fft_pass(float2* buf, int lane, const float2* __
     float2 a[2][8];
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-        const int j = lane + 32 * h2, k = j & (NS - 1);
+        const int j = lane + 32 * h2;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             a[h2][t] = buf[pad(j + 64 * t)];
-            if (NS > 1 && t > 0) a[h2][t] = cmul(a[h2][t], __ldg(&tw512[k * t * (64 / NS)]));
+            // twiddle W512^(k t 64 / Ns) from the [pass][t][j] table: consecutive lanes, consecutive entries
+            if (NS > 1 && t > 0) a[h2][t] = cmul(a[h2][t], __ldg(&tw512[((NS == 8 ? 0 : 8) + t) * 64 + j]));
         }
         dft8(a[h2]);
     }
@@ -185,9 +186,9 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
 #pragma unroll
         for (int mm = 0; mm < kMels / 32; ++mm) {
             const int m = lane + 32 * mm;
-            const int p0 = mel_ptr[m], p1 = mel_ptr[m + 1], b0 = mel_start[m];
+            const int nt = mel_ptr[m], b0 = mel_start[m];
             float acc = 0.f;
-            for (int p = p0; p < p1; ++p) acc = fmaf(mel_w[p], power[b0 + (p - p0)], acc);
+            for (int p = 0; p < nt; ++p) acc = fmaf(__ldg(mel_w + p * kMels + m), power[b0 + p], acc);
             float v;
             if (mode == EGX_LOGMEL_LOG_IN) v = logf(acc + 1e-6f);
             else v = 10.f * log10f(fmaxf(acc, 1e-10f));
