@@ -449,8 +449,11 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
     if (g_gemm_res) {
         if (N % 256 == 0 && num_kb * GemmCfg<256, true>::kBBytes <= kResMaxBytes && (long)m_tiles * (N / 256) >= 4L * g_gemm_sms)
             return launch_bn<256, true>(A, lda, W, ldw, M, N, K, ep, s);
+        // narrower resident slices only where 256-wide tiles are not an option: for N % 256 == 0 with a slice too big
+        // to stay resident (K = 512: the attention output projection) streaming 128 x 256 tiles measured 7% faster
         const int n128 = (N + 127) / 128;
-        if (num_kb * GemmCfg<128, true>::kBBytes <= kResMaxBytes && (long)m_tiles * n128 >= 4L * g_gemm_sms && n128 <= g_gemm_sms)
+        if (N % 256 != 0 && num_kb * GemmCfg<128, true>::kBBytes <= kResMaxBytes && (long)m_tiles * n128 >= 4L * g_gemm_sms &&
+            n128 <= g_gemm_sms)
             return launch_bn<128, true>(A, lda, W, ldw, M, N, K, ep, s);
     }
     if (N % 256 == 0) return launch_bn<256, false>(A, lda, W, ldw, M, N, K, ep, s);

@@ -17,8 +17,9 @@ def eng():
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 256, 256), (1000, 126, 126), (77, 1536, 256),
                                    (64, 256, 8704), (4096, 1024, 256), (129, 8, 64), (5, 64, 256),
-                                   # tall problems take the weights-resident variant (BN 256 / 128, K = 576 slice of 144 KB)
-                                   (40000, 512, 256), (76000, 126, 256), (40000, 256, 576)])
+                                   # tall problems take the weights-resident variant: BN 256; BN 128 where N % 256 != 0
+                                   # (also with a K = 576 slice of 144 KB); N % 256 == 0 with K too long streams 128 x 256 tiles
+                                   (40000, 512, 256), (76000, 126, 256), (40000, 384, 576), (40000, 256, 576)])
 @pytest.mark.parametrize("epi", ["plain", "bias_relu", "addend_mod"])
 def test_linear_tc(eng, m, n, k, epi):
     g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
