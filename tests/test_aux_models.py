@@ -197,3 +197,53 @@ def test_cuda_empty_batches_and_shape_errors():
         sk(torch.zeros(2, 34, 282, device="cuda"))            # post_projector flattens exactly n_position frames
     with pytest.raises(RuntimeError, match="d_k = d_v = 64"):
         mirrors.SkeletonClassifier().eval().cuda()(torch.zeros(1, 60, 242, device="cuda"))   # reference defaults: d_k = 32
+
+
+@pytest.mark.gpu
+def test_evaluation_loop_matches_the_oracle_composition():
+    """emotiongestures_b200.evaluate.GestureEvaluator = test_emotion_gesture_diversity_iterative.py:191-255 (BEAT
+    geometry) without the dataset and the beat metric: sampler -> generator -> skeleton classifier -> FGD features ->
+    mean / covariance, against the same chain built from the oracle restatements on the CPU."""
+    from emotiongestures_b200 import BEAT, Transformer
+    from emotiongestures_b200 import fgd as fgd_mod
+    from emotiongestures_b200.evaluate import GestureEvaluator
+    from oracle import generator as og
+    gen = Transformer.from_config(BEAT).eval()
+    gsd = synth.synth_state_dict(gen.state_dict(), 21)
+    gen.load_state_dict(gsd)
+    vae, vsd = build(mirrors.MLP_Reconstruct_v3, 22)
+    skel, ssd = build(CASES["skeleton"][0], 23, *CASES["skeleton"][2])
+    fgdn, fsd = build(mirrors.FGDNet, 24)
+    ev = GestureEvaluator(gen.cuda(), vae.cuda(), skel.cuda(), fgdn.cuda(), n_pre_poses=BEAT.prior_frames)
+    ref_feats_p, ref_feats_t, ref = [], [], dict(acc=0.0, rot=0.0, l2=0.0)
+    for it in range(2):
+        n = 3
+        spec = torch.from_numpy(synth.synth_spec(n, BEAT.n_mels, BEAT.spec_w, 40 + it))
+        poses = rnd((n, BEAT.frames, BEAT.pose_dim), 41 + it, 1) * 0.3
+        lab = torch.tensor([(it + i) % 8 for i in range(n)])
+        y = torch.nn.functional.one_hot(lab, 8).float()
+        z = rnd((n, 32), 42 + it, 2)
+        text = torch.zeros(n, 60, dtype=torch.int64)
+        pred = ev.step(spec, text, poses, y, z=z).cpu()
+        with torch.no_grad():
+            sampled = oa.cvae3_sample(vsd, y, z)
+            o_pred = og.generator_forward(gsd, BEAT, spec, poses[:, :BEAT.prior_frames], sampled)[0]
+            o_logits, _ = oa.skeleton_classifier(ssd, o_pred)
+            ref_feats_p.append(oa.fgd_latent(fsd, o_pred).reshape(-1, 512))
+            ref_feats_t.append(oa.fgd_latent(fsd, poses).reshape(-1, 512))
+        assert rel_max(pred, o_pred) <= 3e-3
+        ref["acc"] += 100.0 * (o_logits.argmax(1) == lab).double().mean().item()
+        ref["rot"] += (poses.reshape(n, -1, 6) - o_pred.reshape(n, -1, 6)).abs().mean().item()
+        ref["l2"] += (poses - o_pred).norm(dim=-1).mean().item()
+    out = ev.finalize()
+    fp, ft = torch.cat(ref_feats_p).double().numpy(), torch.cat(ref_feats_t).double().numpy()
+    mu_p, sig_p = out["pred_stats"]
+    assert np.allclose(mu_p, fp.mean(0), rtol=0, atol=3e-3 * np.abs(fp).max())
+    assert np.allclose(sig_p, np.cov(fp, rowvar=False), rtol=0, atol=6e-3 * np.abs(np.cov(fp, rowvar=False)).max())
+    mu_t, sig_t = out["target_stats"]
+    assert np.allclose(mu_t, ft.mean(0), rtol=0, atol=3e-3 * np.abs(ft).max())
+    assert abs(out["rotation_error_deg"] - ref["rot"] / 2 * 57.2958) <= 3e-3 * ref["rot"] / 2 * 57.2958
+    assert abs(out["l2_pose"] - ref["l2"] / 2) <= 3e-3 * ref["l2"] / 2
+    assert abs(out["emotion_acc_percent"] - ref["acc"] / 2) <= 34.0          # one flipped argmax of 3 clips at most
+    want = fgd_mod.frechet_distance(fp.mean(0), np.cov(fp, rowvar=False), ft.mean(0), np.cov(ft, rowvar=False))
+    assert np.isfinite(out["fgd"]) and abs(out["fgd"] - want) <= 2e-2 * max(abs(want), 1.0)
