@@ -103,3 +103,25 @@ class GestureEvaluator:
         return {"fgd": _fgd.frechet_distance(mu_p, sig_p, mu_t, sig_t), "emotion_acc_percent": acc / steps,
                 "rotation_error_deg": rot / steps * 57.2958, "l2_pose": l2 / steps,
                 "pred_stats": (mu_p, sig_p), "target_stats": (mu_t, sig_t)}
+
+
+def diversity_score(activations, rng=None):
+    """model/FHD_score.py:244-280 (`diversity_score` + `calculate_diversity`): ten estimates of the mean L2 distance
+    between five random pairs of clips' feature blocks, summarised as the centre and the bounds of the 95% normal
+    interval.  `activations`: (N, 60, 512) (or anything that reshapes to it, as the reference does) tensor or array;
+    `rng`: an object with numpy's `randint(low, high, size)` — the reference draws from the unseeded global
+    `np.random`, so pass `np.random.RandomState(seed)` for a reproducible score.  Returns (score, (lo, hi))."""
+    import numpy as np
+    from scipy import stats
+    rng = np.random if rng is None else rng
+    act = torch.as_tensor(activations).reshape(-1, 60, 512)
+    n = act.shape[0]
+    window = np.empty((10, 1))
+    for i in range(10):
+        first = rng.randint(0, n, 5)
+        second = rng.randint(0, n, 5)
+        d = sum(torch.dist(act[int(a)], act[int(b)]) for a, b in zip(first, second)) / 5
+        window[i] = np.float32(float(d))
+    mean, std = np.mean(window, axis=0), np.std(window, axis=0)
+    interval = stats.norm.interval(0.95, mean, std)
+    return (interval[0] + interval[1]) / 2, interval

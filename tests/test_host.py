@@ -88,3 +88,15 @@ def test_dropin_reads_the_geometry_of_both_generator_variants():
         for f in ("frames", "prior_frames", "pose_dim", "d_model", "d_inner", "n_layers", "n_head", "d_k", "d_v", "spec_w",
                   "n_position"):
             assert getattr(got, f) == getattr(cfg, f), (type(m).__name__, f)
+
+
+def test_diversity_score_matches_the_reference_golden():
+    """evaluate.diversity_score vs model/FHD_score.py:244-280 run on the same array with np.random.seed(123)
+    (tests/golden/diversity.npz, made in the build container against the real reference)."""
+    import numpy as np
+    from emotiongestures_b200.evaluate import diversity_score
+    from tests.helpers import load_golden
+    g = load_golden("diversity")
+    x = np.random.default_rng(int(g["data_seed"])).standard_normal((int(g["n"]) * 60, 512)).astype(np.float32)
+    score, (lo, hi) = diversity_score(x, np.random.RandomState(int(g["seed"])))
+    assert np.allclose(score, g["score"], rtol=1e-6) and np.allclose(lo, g["lo"], rtol=1e-6) and np.allclose(hi, g["hi"], rtol=1e-6)
