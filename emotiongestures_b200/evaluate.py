@@ -100,7 +100,10 @@ class GestureEvaluator:
         mu_p, sig_p = _fgd.finalize_stats(self.acc_pred, self.dim, self.shift)
         mu_t, sig_t = _fgd.finalize_stats(self.acc_target, self.dim, self.shift)
         steps, acc, rot, l2 = (float(v) for v in self.sums.cpu())
-        return {"fgd": _fgd.frechet_distance(mu_p, sig_p, mu_t, sig_t), "emotion_acc_percent": acc / steps,
+        # the Frechet tail stays on the device (float64 eigh); the host version is the cross-check in the tests
+        fgd_dev = _fgd.frechet_distance_device(*_fgd.finalize_stats_device(self.acc_pred, self.dim, self.shift),
+                                               *_fgd.finalize_stats_device(self.acc_target, self.dim, self.shift))
+        return {"fgd": fgd_dev, "fgd_host": _fgd.frechet_distance(mu_p, sig_p, mu_t, sig_t), "emotion_acc_percent": acc / steps,
                 "rotation_error_deg": rot / steps * 57.2958, "l2_pose": l2 / steps,
                 "pred_stats": (mu_p, sig_p), "target_stats": (mu_t, sig_t)}
 

@@ -69,3 +69,36 @@ def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
         return 100
     d = mu1 - mu2
     return float(d @ d + np.trace(sigma1) + np.trace(sigma2) - 2.0 * tr)
+
+
+def finalize_stats_device(acc: torch.Tensor, dim: int, shift=None):
+    """`finalize_stats` without leaving the device: (mu (D,), sigma (D,D)) as float64 tensors."""
+    n = acc[0]
+    m = acc[1:1 + dim] / n
+    g = acc[1 + dim:].reshape(dim, dim)
+    sigma = (g - n * torch.outer(m, m)) / (n - 1.0)
+    sigma = 0.5 * (sigma + sigma.T)
+    return (m + shift if shift is not None else m), sigma
+
+
+def frechet_distance_device(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """`frechet_distance` on the GPU: the symmetric form sqrt(S1) S2 sqrt(S1) through two
+    float64 `torch.linalg.eigh` calls (cuSOLVER — a library eigensolver for a once-per-evaluation D x D problem, not
+    a hot-path kernel), same conventions as the host version: eps*I retry on a non-finite trace, sentinel 100 when
+    the product has an eigenvalue below -1e-6.  Returns a Python float."""
+    def trace_sqrt(s1, s2):
+        w, v = torch.linalg.eigh(s1)
+        root = (v * w.clamp_min(0).sqrt()) @ v.T
+        lam = torch.linalg.eigvalsh(root @ s2 @ root)
+        return lam.clamp_min(0).sqrt().sum(), lam.min()
+
+    mu1, mu2 = mu1.double(), mu2.double()
+    sigma1, sigma2 = sigma1.double(), sigma2.double()
+    tr, lam_min = trace_sqrt(sigma1, sigma2)
+    if not bool(torch.isfinite(tr)):
+        off = torch.eye(sigma1.shape[0], dtype=torch.float64, device=sigma1.device) * eps
+        tr, lam_min = trace_sqrt(sigma1 + off, sigma2 + off)
+    if not bool(torch.isfinite(tr)) or float(lam_min) < -1e-6:
+        return 100
+    d = mu1 - mu2
+    return float(d @ d + torch.trace(sigma1) + torch.trace(sigma2) - 2.0 * tr)

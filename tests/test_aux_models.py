@@ -247,3 +247,4 @@ def test_evaluation_loop_matches_the_oracle_composition():
     assert abs(out["emotion_acc_percent"] - ref["acc"] / 2) <= 34.0          # one flipped argmax of 3 clips at most
     want = fgd_mod.frechet_distance(fp.mean(0), np.cov(fp, rowvar=False), ft.mean(0), np.cov(ft, rowvar=False))
     assert np.isfinite(out["fgd"]) and abs(out["fgd"] - want) <= 2e-2 * max(abs(want), 1.0)
+    assert abs(out["fgd"] - out["fgd_host"]) <= 1e-6 * max(abs(want), 1.0)      # device eigh tail == host numpy tail

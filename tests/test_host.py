@@ -100,3 +100,27 @@ def test_diversity_score_matches_the_reference_golden():
     x = np.random.default_rng(int(g["data_seed"])).standard_normal((int(g["n"]) * 60, 512)).astype(np.float32)
     score, (lo, hi) = diversity_score(x, np.random.RandomState(int(g["seed"])))
     assert np.allclose(score, g["score"], rtol=1e-6) and np.allclose(lo, g["lo"], rtol=1e-6) and np.allclose(hi, g["hi"], rtol=1e-6)
+
+
+def test_frechet_distance_device_variant_matches_the_host_tail():
+    """fgd.frechet_distance_device (torch.linalg.eigh, float64; runs on the CPU here, on the GPU in the evaluator)
+    == fgd.frechet_distance (numpy) == the closed form for commuting covariances, incl. the rank-deficient case."""
+    import numpy as np
+    import torch
+    from emotiongestures_b200 import fgd
+    rng = np.random.default_rng(3)
+    for n, d in ((400, 16), (10, 16)):                      # full rank, and fewer samples than dimensions
+        a, b = rng.standard_normal((n, d)), rng.standard_normal((n, d)) * 1.5 + 0.3
+        m1, s1, m2, s2 = a.mean(0), np.cov(a, rowvar=False), b.mean(0), np.cov(b, rowvar=False)
+        host = fgd.frechet_distance(m1, s1, m2, s2)
+        dev = fgd.frechet_distance_device(*(torch.from_numpy(x) for x in (m1, s1, m2, s2)))
+        assert abs(host - dev) <= 1e-8 * max(1.0, abs(host))
+    s = np.diag([1.0, 4.0, 9.0])
+    want = 3 * 0.25 + (1 + 4 + 9) * (1 + 4 - 2 * 2)             # mu diff 0.5 each; Tr(S + 4S - 2 sqrt(4 S^2)) = Tr S
+    got = fgd.frechet_distance_device(torch.zeros(3), torch.from_numpy(s), torch.full((3,), 0.5), torch.from_numpy(4 * s))
+    assert abs(got - want) <= 1e-9
+    acc = torch.zeros(1 + 3 + 9, dtype=torch.float64)
+    x = torch.from_numpy(rng.standard_normal((50, 3)))
+    acc[0], acc[1:4], acc[4:] = 50, x.sum(0), (x.T @ x).reshape(-1)
+    mu, sig = fgd.finalize_stats_device(acc, 3)
+    assert torch.allclose(mu, x.mean(0)) and torch.allclose(sig, torch.from_numpy(np.cov(x.numpy(), rowvar=False)))
