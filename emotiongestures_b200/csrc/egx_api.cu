@@ -1367,6 +1367,14 @@ int egx_finalize_weights(egx_handle* h) {
         if (!fold_bn(h, k_b1, Fc, s1, t1) || !fold_bn(h, k_b2, Fc, s2, t2)) return 1;
         w.p_c1w = upload(h, c1w->v); w.p_c1b = upload(h, c1b->v); w.p_s1 = upload(h, s1); w.p_t1 = upload(h, t1);
         w.p_c2w = upload(h, c2w->v); w.p_c2b = upload(h, c2b->v); w.p_s2 = upload(h, s2); w.p_t2 = upload(h, t2);
+        {
+            const int F4c = (Fc + 3) & ~3;
+            std::vector<float> wt((size_t)Fc * 3 * F4c, 0.f);
+            for (int f = 0; f < Fc; ++f)
+                for (int ci = 0; ci < Fc; ++ci)
+                    for (int k = 0; k < 3; ++k) wt[((size_t)ci * 3 + k) * F4c + f] = c2w->v[((size_t)f * Fc + ci) * 3 + k];
+            w.p_c2wt = upload(h, wt);
+        }
     }
     if (memory) {
         const HostTensor* sw = find(h, pe + "spatial_memory.spatial_chunk_encoder.0.weight");

@@ -78,6 +78,7 @@ struct Weights {
     // prior encoder
     float *p_c1w = nullptr, *p_c1b = nullptr, *p_s1 = nullptr, *p_t1 = nullptr;
     float *p_c2w = nullptr, *p_c2b = nullptr, *p_s2 = nullptr, *p_t2 = nullptr;
+    float* p_c2wt = nullptr;          // conv2 weights as the kernel stages them: [cin][tap][cout padded to 4], zero padded
     LinearW p_fc1, p_fc2;             // Prior_ConvEncoder fc1 / fc2, or Prior_MemoryEncoder post_header.0 / .2
     MemPriorW mem;
     LinearW emo0, emo2, sem0, sem2, fus0, fus2;

@@ -187,10 +187,9 @@ prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
     float* sin_ = w2s + F * 3 * F4;   // [p][P+2] zero-padded
     float* mid = sin_ + p * PW;       // [F][P+2] zero-padded
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < F * 3 * F4; i += blockDim.x) {
-        const int f = i % F4, k = (i / F4) % 3, c = i / (3 * F4);
-        w2s[i] = f < F ? w2[(f * F + c) * 3 + k] : 0.f;
-    }
+    // conv2 weights arrive already in the staged [c][k][f] layout (host-side transpose): a linear 16-byte copy
+    for (int i = threadIdx.x; i < F * 3 * F4 / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(w2s)[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
     for (int i = threadIdx.x; i < p * PW; i += blockDim.x) {
         const int c = i / PW, x = i % PW - 1;
         sin_[i] = (x >= 0 && x < P) ? prior[((size_t)b * p + c) * P + x] : 0.f;
@@ -301,7 +300,7 @@ int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F,
     if (cudaFuncSetAttribute(prior_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -1;
     prior_conv_kernel<T><<<B, 256, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,
-                                              w.p_c2w, w.p_c2b, w.p_s2, w.p_t2, out, ldo);
+                                              w.p_c2wt, w.p_c2b, w.p_s2, w.p_t2, out, ldo);
     return ok() ? 1 : -1;
 }
 template int launch_prior_conv<float>(const Weights&, const float*, int, int, int, int, float*, int, cudaStream_t);
