@@ -153,7 +153,7 @@ def main():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if "--emotion-net" not in sys.argv and "--skeleton" not in sys.argv:
+    if not {"--emotion-net", "--skeleton", "--diversity"} & set(sys.argv):
         main()
     for f in sorted(os.listdir(GOLD)):
         if f.startswith("aux_"):
@@ -211,7 +211,28 @@ def skeleton_golden():
                         mid=r_mid.numpy().astype(np.float32))
 
 
+def diversity_golden():
+    """model/FHD_score.py:244-280 diversity_score on a seeded array with np.random.seed(123): the reference draws its
+    clip pairs from the global numpy RNG, so the same seed through np.random.RandomState reproduces it."""
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("fasttext", types.ModuleType("fasttext"))
+    import importlib
+    from emotiongestures_b200.evaluate import diversity_score
+    ref = importlib.import_module("model.FHD_score")
+    n = 37
+    x = np.random.default_rng(5).standard_normal((n * 60, 512)).astype(np.float32)
+    np.random.seed(123)
+    r_score, r_int = ref.diversity_score(x.copy(), "cpu")
+    m_score, m_int = diversity_score(x, np.random.RandomState(123))
+    assert np.allclose(r_score, m_score) and np.allclose(r_int[0], m_int[0]) and np.allclose(r_int[1], m_int[1])
+    print(f"  diversity: reference {float(r_score[0]):.6f} mirror {float(m_score[0]):.6f}")
+    np.savez_compressed(os.path.join(GOLD, "diversity.npz"), seed=123, data_seed=5, n=n, score=np.asarray(r_score),
+                        lo=np.asarray(r_int[0]), hi=np.asarray(r_int[1]))
+
+
 if __name__ == "__main__" and "--emotion-net" in sys.argv:
     emotion_net_golden()
+if __name__ == "__main__" and "--diversity" in sys.argv:
+    diversity_golden()
 if __name__ == "__main__" and "--skeleton" in sys.argv:
     skeleton_golden()
