@@ -255,7 +255,7 @@ def run_own_arm(args):
 
     def e2e_step():
         # public API: pinned host in -> pinned host out, chunked so PCIe copies overlap the kernels
-        eng.infer_host(h_audio, h_prior, h_poses, chunk=args.e2e_chunk, poses_dev=d_poses)
+        eng.infer_host(h_audio, h_prior, h_poses, chunk=args.e2e_chunk, mode=LOGMEL_LOG_IN, preemph=True, poses_dev=d_poses)
         if world > 1:
             dist.all_gather(gathered, d_poses)
 
@@ -281,7 +281,7 @@ def run_own_arm(args):
         small = {}
         for nb in (1, 8):
             a, p_ = audio[:nb].contiguous(), prior[:nb].contiguous()
-            path = eng.capture(nb)
+            path = eng.capture(nb, LOGMEL_LOG_IN, True)
             res = {}
             for name, fn in (("eager", lambda: step(a, p_)), ("graph", lambda: path(a, p_))):
                 for _ in range(10):

@@ -8,12 +8,12 @@ Public surface:
   GeneratorConfig, TED, BEAT
   fgd                    FGD statistics (mean/covariance) + NCCL all-reduce
 """
-from .config import (BEAT, LOGMEL_DB, LOGMEL_LOG_IN, TED, GeneratorConfig, audio_length,
-                     spectrogram_length)
+from .config import (BEAT, LOGMEL_DB, LOGMEL_FP16_STORAGE, LOGMEL_LOG_IN, LOGMEL_REFERENCE, TED, GeneratorConfig,
+                     audio_length, spectrogram_length)
 from .generator import MemoryTransformer, Transformer, randomize_norm_stats_
 
 __all__ = ["Transformer", "MemoryTransformer", "install", "Engine", "GeneratorConfig", "TED", "BEAT", "LOGMEL_DB",
-           "LOGMEL_LOG_IN", "audio_length", "spectrogram_length", "randomize_norm_stats_"]
+           "LOGMEL_LOG_IN", "LOGMEL_FP16_STORAGE", "LOGMEL_REFERENCE", "audio_length", "spectrogram_length", "randomize_norm_stats_"]
 
 
 def __getattr__(name):

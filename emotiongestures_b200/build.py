@@ -43,8 +43,22 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, attribution: bool | None = None) -> str:
+    """attribution=True (or EGX_ATTRIBUTION=1 in the environment of the BUILD) compiles the EGX_* variant /
+    attribution switches in; the shipped library has none (csrc/egx_common.cuh: env_switch)."""
     nvcc = _nvcc()
+    if attribution is None:
+        attribution = os.environ.get("EGX_ATTRIBUTION") == "1"
+    flags = NVCC_FLAGS + (["-DEGX_ATTRIBUTION"] if attribution else [])
+    stamp = os.path.join(OBJ_DIR, ".attribution")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    was = os.path.exists(stamp)
+    if was != bool(attribution):
+        force = True
+        if attribution:
+            open(stamp, "w").close()
+        else:
+            os.remove(stamp)
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "egx.h"))
@@ -55,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = pair
         if not force and not _stale(obj, [src] + headers):
             return ""
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -76,5 +90,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                 attribution=True if "--attribution" in sys.argv else None)
     print(path)

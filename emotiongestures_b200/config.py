@@ -24,6 +24,15 @@ DB_TOP = 80.0         # librosa.power_to_db default
 
 LOGMEL_DB = 0         # F4a: power_to_db(ref=max), utils/data_utils.py:37
 LOGMEL_LOG_IN = 1     # F4b: log(x+1e-6) + InstanceNorm1d, model/ResNetSE34V2.py:96-98
+LOGMEL_FP16_STORAGE = 0x100   # OR-ed into LOGMEL_DB: the astype('float16') storage cast of utils/data_utils.py:38
+# The features the reference's checkpoints were trained on and its loaders deliver (utils/data_utils.py:35-39, re-read as
+# fp32 at data_loader/lmdb_data_loader_expressive.py:204): no pre-emphasis, power_to_db(ref=max), fp16 storage rounding.
+# This is the default of every raw-audio entry point.  One documented difference remains: the reference takes ref=max
+# over the whole recording it extracted features from and then slices clips out of it, while a per-clip front-end
+# takes the max over the clip handed in, so a clip quieter than its recording's peak comes out shifted by a constant
+# (and floored 80 dB below its own peak instead of the recording's).  Callers that have the recording's peak can
+# add `10*log10(clip_max/recording_max)` to the result.
+LOGMEL_REFERENCE = LOGMEL_DB | LOGMEL_FP16_STORAGE
 
 
 def spectrogram_length(n_frames: int, fps: int) -> int:

@@ -18,10 +18,15 @@ constexpr float kBnEps = 1e-5f;    // torch.nn.BatchNorm default; the reference 
 // ---------------------------------------------------------------------------------------------
 template <class T>
 T* upload(egx_handle* h, const std::vector<T>& v) {
+    // a failed allocation / copy is recorded as a null entry of the owning list, which the packers check before they
+    // declare a family ready (egx_finalize_weights, BucketScope::ok): no kernel ever sees a null weight pointer
     void* p = nullptr;
-    if (cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)) != cudaSuccess) return nullptr;
-    if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
-        return nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)) != cudaSuccess) p = nullptr;
+    if (p && !v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(p);
+        p = nullptr;
+    }
+    if (!p) { cudaGetLastError(); h->upload_failed = true; }
     (h->cur_bucket ? *h->cur_bucket : h->owned).push_back(p);
     return static_cast<T*>(p);
 }
@@ -646,7 +651,7 @@ struct TrunkBufs {
 
 // EGX_SE_FUSED=0 (attribution experiments only) restores the separate gate*y + residual pass over the map
 bool se_fused() {
-    static const bool on = [] { const char* e = getenv("EGX_SE_FUSED"); return !e || atoi(e) != 0; }();
+    static const bool on = env_switch("EGX_SE_FUSED", 1) != 0;
     return on;
 }
 
@@ -792,8 +797,7 @@ int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const
 // clips per chunk of the transformer tail: a multiple of 6 (3 TED / 2 BEAT clips share an attention tile)
 int tail_chunk_clips() {
     static const int n = [] {
-        const char* e = getenv("EGX_TAIL_CHUNK");
-        const int v = e ? atoi(e) : 0;
+        const int v = env_switch("EGX_TAIL_CHUNK", 0);
         return v <= 0 ? (1 << 30) / 6 * 6 : std::max(6, v / 6 * 6);
     }();
     return n;
@@ -1446,10 +1450,23 @@ int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, in
     if (n_cols < 1 || n_cols > 1 + n_samples / 512) EGX_FAIL(h, "n_cols out of range for n_samples");
     if (n_cols > 256) EGX_FAIL(h, "n_cols > 256 not supported (shared-memory tile)");
     if (n_samples < 2) EGX_FAIL(h, "need at least 2 samples");
-    if (mode != EGX_LOGMEL_DB && mode != EGX_LOGMEL_LOG_IN) EGX_FAIL(h, "unknown log-mel mode");
+    if (mode != EGX_LOGMEL_DB && mode != EGX_LOGMEL_LOG_IN && mode != (EGX_LOGMEL_DB | EGX_LOGMEL_FP16_STORAGE))
+        EGX_FAIL(h, "unknown log-mel mode");
     cudaStream_t s = (cudaStream_t)stream;
     StageScope sc(h, 1);
     LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, s));
+    return 0;
+}
+
+int egx_audio_fixed_length(egx_handle* h, const float* samples, const int64_t* offsets, int n_clips, int n_out,
+                           float* out, void* stream) {
+    if (!h) return 1;
+    if (n_clips <= 0) return 0;
+    if (!samples || !offsets || !out) EGX_FAIL(h, "null pointer argument");
+    if (n_out < 1) EGX_FAIL(h, "n_out must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    StageScope sc(h, 1);
+    LAUNCH(h, launch_fixed_length(samples, offsets, n_clips, n_out, out, s));
     return 0;
 }
 

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -175,6 +176,7 @@ struct egx_handle {
     egx::Weights w;
     egx::LogmelTables lm;
     bool finalized = false;                            // generator weights packed
+    bool upload_failed = false;                        // a weight upload failed (its list entry is null)
     egx::CvaeW cvae;
     egx::Cvae3W cvae3;
     egx::PoseEncW motion_ae, pose_enc;
@@ -211,11 +213,26 @@ namespace egx {
 
 inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
 
+// Variant / attribution switches (EGX_* environment variables) exist only in builds made with -DEGX_ATTRIBUTION
+// (python -m emotiongestures_b200.build --attribution): the shipped library never reads the environment, so a stray
+// variable cannot change which kernels run or — for the EGX_*_DEBUG bits, which skip work — corrupt results.
+inline int env_switch(const char* name, int dflt) {
+#ifdef EGX_ATTRIBUTION
+    if (const char* e = getenv(name)) return atoi(e);
+#else
+    (void)name;
+#endif
+    return dflt;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel launchers (each returns the number of kernels it enqueued, or <0 on launch error)
 // ---------------------------------------------------------------------------------------------
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
                   int preemph, float* out, cudaStream_t s);
+
+// F5: ragged clips (back to back in `samples`, clip b = [offsets[b], offsets[b+1])) -> (B, N), cropped or symmetric-padded
+int launch_fixed_length(const float* samples, const int64_t* offsets, int B, int N, float* out, cudaStream_t s);
 
 template <class T>
 int launch_stem(const ConvW& c, const float* spec, int B, int H, int W, T* out, cudaStream_t s);

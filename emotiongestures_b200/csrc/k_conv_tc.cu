@@ -991,10 +991,10 @@ int conv_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (const char* e = getenv("EGX_CONV_HALO")) g_halo = atoi(e);
-    if (const char* e = getenv("EGX_CONV_DEBUG")) g_debug = atoi(e);
-    if (const char* e = getenv("EGX_CONV_OUT")) g_out_direct = atoi(e);
-    if (const char* e = getenv("EGX_CONV_CONTIG")) g_contig = atoi(e);
+    g_halo = env_switch("EGX_CONV_HALO", g_halo);
+    g_debug = env_switch("EGX_CONV_DEBUG", 0);
+    g_out_direct = env_switch("EGX_CONV_OUT", g_out_direct);
+    g_contig = env_switch("EGX_CONV_CONTIG", g_contig);
     int rc = 0;
     rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
     rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;

@@ -420,9 +420,9 @@ int gemm_tc_init_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (const char* e = getenv("EGX_GEMM_RES")) g_gemm_res = atoi(e);
-    if (const char* e = getenv("EGX_GEMM_TMA_STORE")) g_gemm_tma_store = atoi(e);
-    if (const char* e = getenv("EGX_GEMM_DEBUG")) g_gemm_debug = atoi(e);
+    g_gemm_res = env_switch("EGX_GEMM_RES", g_gemm_res);
+    g_gemm_tma_store = env_switch("EGX_GEMM_TMA_STORE", g_gemm_tma_store);
+    g_gemm_debug = env_switch("EGX_GEMM_DEBUG", 0);
     const int res_max = 227 * 1024;
     if (cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;

@@ -13,6 +13,8 @@
 // tile (still in L2, 36 KB per clip) and it is normalised in place.  Keeping the tile out of shared
 // memory lets three CTAs share an SM (the kernel is latency-bound: every FFT pass is a shared-memory
 // round trip).  Algorithmic HBM traffic 4*N + 4*128*W bytes per clip.
+#include <algorithm>
+
 #include "egx_common.cuh"
 
 namespace egx {
@@ -119,6 +121,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
     __shared__ float s_red[kMaxWarps];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const bool log_in = (mode & 0xff) == EGX_LOGMEL_LOG_IN, f16_round = (mode & EGX_LOGMEL_FP16_STORAGE) != 0;
     const float* x = audio + (size_t)blockIdx.x * N;
     float2* buf = fftbuf + warp * kBufLen;
     float* tile = out + (size_t)blockIdx.x * kMels * n_cols;             // raw log values, normalised in place below
@@ -190,7 +193,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
             float acc = 0.f;
             for (int p = 0; p < nt; ++p) acc = fmaf(__ldg(mel_w + p * kMels + m), power[b0 + p], acc);
             float v;
-            if (mode == EGX_LOGMEL_LOG_IN) v = logf(acc + 1e-6f);
+            if (log_in) v = logf(acc + 1e-6f);
             else v = 10.f * log10f(fmaxf(acc, 1e-10f));
             tile[m * n_cols + t] = v;
         }
@@ -199,7 +202,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
     __syncthreads();        // CTA-scope visibility of the tile written above (global memory, same CTA)
 
     float* o = tile;
-    if (mode == EGX_LOGMEL_LOG_IN) {
+    if (log_in) {
         // InstanceNorm1d: per (clip, mel) over time, biased variance, eps 1e-5, no affine
         for (int m = warp; m < kMels; m += n_warps) {
             const float* row = tile + m * n_cols;
@@ -220,8 +223,30 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
         __syncthreads();
         mx = s_red[0];
         for (int w = 1; w < n_warps; ++w) mx = fmaxf(mx, s_red[w]);
-        for (int i = threadIdx.x; i < kMels * n_cols; i += blockDim.x)
-            o[i] = fmaxf(tile[i] - mx, -80.f);
+        // astype('float16') of utils/data_utils.py:38 (the features are stored as fp16 and re-read as fp32,
+        // data_loader/lmdb_data_loader_expressive.py:204): optional, applied after the comparison point of the 1e-4 gate
+        for (int i = threadIdx.x; i < kMels * n_cols; i += blockDim.x) {
+            const float v = fmaxf(tile[i] - mx, -80.f);
+            o[i] = f16_round ? __half2float(__float2half_rn(v)) : v;
+        }
+    }
+}
+
+// F5 — make_audio_fixed_length (utils/data_utils.py:69-75): crop to N samples, or extend at the end with
+// np.pad(mode='symmetric') (the signal mirrored about its last sample, edge repeated; period 2 n for pads longer than
+// the clip).  Ragged clips arrive back to back in `samples`; clip b is samples[offsets[b] .. offsets[b+1]).
+__global__ void fixed_length_kernel(const float* __restrict__ samples, const int64_t* __restrict__ offsets, int N,
+                                    float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int64_t lo = offsets[b], n = offsets[b + 1] - lo;
+    float* o = out + (size_t)b * N;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N; t += gridDim.x * blockDim.x) {
+        float v = 0.f;                       // an empty clip has nothing to mirror (np.pad raises; here: silence)
+        if (n > 0) {
+            const int64_t u = t % (2 * n);
+            v = __ldg(samples + lo + (u < n ? u : 2 * n - 1 - u));
+        }
+        o[t] = v;
     }
 }
 
@@ -234,15 +259,24 @@ int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n
     for (int w = kMaxWarps; w >= 9; --w)
         if ((n_cols + w - 1) / w * w < (n_cols + warps - 1) / warps * warps) warps = w;
     const size_t smem = sizeof(float2) * warps * kBufLen;
-    static size_t configured = 0;
-    if (smem > configured) {
+    // opt-in shared-memory size is a per-device function attribute (one handle per device may live in one process)
+    static size_t configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (smem > configured[dev]) {
         if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess) return -1;
-        configured = smem;
+        configured[dev] = smem;
     }
     logmel_kernel<<<B, warps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window,
                                                 t.tw512, t.tw1024, t.mel_start, t.mel_ptr,
                                                 t.mel_w);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_fixed_length(const float* samples, const int64_t* offsets, int B, int N, float* out, cudaStream_t s) {
+    const dim3 grid((unsigned)std::min(cdiv(N, 256 * 4), 64), (unsigned)B);
+    fixed_length_kernel<<<grid, 256, 0, s>>>(samples, offsets, N, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -1,13 +1,14 @@
 """`install(generator)`: put libegx behind a LIVE reference generator.
 
 `generator` is the reference's own Full_model.Models.Transformer (or
-Models_memory.Transformer, possibly unwrapped from nn.DataParallel), already
+Models_memory.Transformer), bare or wrapped in nn.DataParallel, already
 `.eval()`-ed and on a CUDA device, exactly as
 test_emotion_gesture_diversity_iterative.py:135-145 leaves it.  Its `forward` is
-swapped for one that keeps the signature and the 5-tuple but routes the pose path
-through the C ABI; the text encoder (dead w.r.t. poses) keeps running as the
-module's own PyTorch sub-module.  In training mode the module's original forward is
-called untouched (the library is inference-only).
+overridden (at class level, so DataParallel replicas get it too) by one that keeps the
+signature and the 5-tuple but routes the pose path through the C ABI on the device the
+call runs on; the text encoder (dead w.r.t. poses) keeps running as the module's own
+PyTorch sub-module.  In training mode the module's original forward is called untouched
+(the library is inference-only).
 """
 from __future__ import annotations
 
@@ -48,25 +49,44 @@ def config_from_module(gen) -> GeneratorConfig:
 
 
 def install(gen: torch.nn.Module, precision: str = "tc", spec_w: int | None = None):
-    """Swap `gen.forward` for the libegx path; returns the Engine (call `.load_state_dict`
-    on it again, or `gen.egx_sync()`, after loading a new checkpoint)."""
-    cfg = config_from_module(gen)
+    """Route the pose path of a live reference generator through libegx; returns the device-0 Engine.
+
+    `gen` may be the bare module or an `nn.DataParallel` wrapper around it (the evaluation script wraps the generator
+    whenever several GPUs are visible, test_emotion_gesture_diversity_iterative.py:137-138).  The module's class is
+    swapped for a subclass of itself that overrides `forward` — a class-level method, because DataParallel rebuilds
+    its replicas on every call as shallow copies of the instance (`type(self).__new__` + `__dict__.copy()`), so an
+    instance-bound forward would make every replica call the ORIGINAL module on device 0.  The engines live in an
+    `EngineSet` inside the instance `__dict__`, shared by reference with all replicas and keyed by device: each
+    replica thread uses the handle of the GPU its inputs were scattered to.  After loading a new checkpoint call
+    `module.egx_sync()`.  In training mode the reference's own forward runs untouched (the library is inference-only).
+    """
+    from .generator import EngineSet, _call_device
+    module = gen.module if isinstance(gen, torch.nn.DataParallel) else gen
+    if getattr(type(module), "_egx_installed", False):
+        raise RuntimeError("install() was already applied to this module")
+    cfg = config_from_module(module)
     if spec_w is not None:
         cfg = GeneratorConfig(**{**cfg.__dict__, "spec_w": spec_w})
-    dev = next(gen.parameters()).device
-    eng = Engine(cfg, dev, precision=precision)
-    eng.load_state_dict(gen.state_dict())
-    original = gen.forward
+    dev = next(module.parameters()).device
+    base = type(module)
 
     def forward(self, input_spectrum, text, prior_seq, sampled_emotion_feature=None):
         if self.training:
             args = (input_spectrum, text, prior_seq)
-            return original(*args) if sampled_emotion_feature is None else original(*args, sampled_emotion_feature)
+            return (base.forward(self, *args) if sampled_emotion_feature is None
+                    else base.forward(self, *args, sampled_emotion_feature))
+        dev_ = _call_device(self, input_spectrum) or next(self.parameters()).device
+        eng = self._egx_set.get(dev_, self._egx_precision)
         text_embedding = self.text_encoder(text)
         poses, emo, sem, logits = eng.generator_forward(input_spectrum, prior_seq, sampled_emotion_feature)
         return poses, emo, sem, logits, text_embedding
 
-    gen.forward = types.MethodType(forward, gen)
-    gen.egx_engine = eng
-    gen.egx_sync = lambda: eng.load_state_dict(gen.state_dict())
+    patched = type(base.__name__, (base,), {"forward": forward, "_egx_installed": True, "__module__": base.__module__,
+                                            "egx_sync": lambda self: self._egx_set.sync()})
+    engines = EngineSet(module, cfg)
+    eng = engines.get(dev, precision)        # fails loudly here (no library / not sm_100 / CPU module), module untouched
+    module.__dict__["_egx_set"] = engines
+    module.__dict__["_egx_precision"] = precision
+    module.__dict__["egx_engine"] = eng
+    module.__class__ = patched
     return eng

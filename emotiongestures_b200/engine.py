@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .config import LOGMEL_LOG_IN, GeneratorConfig
+from .config import LOGMEL_REFERENCE, GeneratorConfig
 
 _PREC = {"fp32": _lib.EGX_PREC_FP32, "tc": _lib.EGX_PREC_TC}
 
@@ -49,6 +49,7 @@ class Engine:
         self._h = h
         self._ws = None
         self._ws_clips = 0
+        self.batch_coupled = False
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -93,10 +94,14 @@ class Engine:
     def load_state_dict(self, sd):
         """Hand every float tensor of a reference-layout state_dict to the library."""
         with torch.cuda.device(self.device):
-            for k, v in sd.items():
-                if not v.is_floating_point():
-                    continue
-                t = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            # Models_memory.Transformer (Prior_MemoryEncoder): its temporal memory sums over the clips of one call
+            self.batch_coupled = "prior_seq_encoder.pred_conv.0.weight" in sd
+            staged = {k: v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                      for k, v in sd.items() if v.is_floating_point()}
+            # egx_set_weight copies synchronously on the legacy default stream, which does not order against a
+            # non-blocking torch stream that may still be producing the fp32 copies above
+            torch.cuda.current_stream(self.device).synchronize()
+            for k, t in staged.items():
                 shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
                 self._check(self.lib.egx_set_weight(self._h, k.encode(), _ptr(t), shape, t.dim(),
                                                     _lib.EGX_DTYPE_F32), f"egx_set_weight({k})")
@@ -111,8 +116,27 @@ class Engine:
         return self._ws
 
     # -- hot path ----------------------------------------------------------------
-    def logmel(self, audio, mode: int = LOGMEL_LOG_IN, preemph: bool = True, n_cols=None):
-        """(B,N) 16 kHz audio -> (B,128,n_cols) log-mel (F1–F4)."""
+    def fixed_length_audio(self, clips, n_samples=None):
+        """F5 (utils/data_utils.py:69-75): a list of ragged 1-D clips -> (B, n_samples) f32 on the device, each clip
+        cropped or symmetric-padded at its end; the `audio` argument of `logmel`."""
+        n_out = self.cfg.n_audio if n_samples is None else int(n_samples)
+        lens = [int(c.numel()) for c in clips]
+        if any(n == 0 for n in lens):
+            raise RuntimeError("fixed_length_audio: empty clip (np.pad cannot mirror an empty signal either)")
+        out = torch.empty((len(clips), n_out), dtype=torch.float32, device=self.device)
+        if not clips:
+            return out
+        flat = torch.cat([self._f32(c.reshape(-1), "clip") for c in clips])
+        offs = torch.tensor([0] + lens, dtype=torch.int64).cumsum(0).to(self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_audio_fixed_length(self._h, _ptr(flat), _ptr(offs), len(clips), n_out, _ptr(out),
+                                                        self._stream()), "egx_audio_fixed_length")
+        return out
+
+    def logmel(self, audio, mode: int = LOGMEL_REFERENCE, preemph: bool = False, n_cols=None):
+        """(B,N) 16 kHz audio -> (B,128,n_cols) log-mel (F1–F4).  Defaults = the reference's live features
+        (config.LOGMEL_REFERENCE); the north star's PreEmphasis + log + InstanceNorm recipe is
+        `mode=LOGMEL_LOG_IN, preemph=True`."""
         a = self._f32(audio, "audio")
         if a.dim() != 2:
             raise RuntimeError("audio must be (B, N)")
@@ -159,8 +183,8 @@ class Engine:
         self._last_b = b
         return poses, emo, sem, logits
 
-    def infer_host(self, audio_h, prior_h, poses_h, chunk: int = 512, mode: int = LOGMEL_LOG_IN,
-                   preemph: bool = True, poses_dev=None):
+    def infer_host(self, audio_h, prior_h, poses_h, chunk: int = 512, mode: int = LOGMEL_REFERENCE,
+                   preemph: bool = False, poses_dev=None):
         """End-to-end batch from PINNED host buffers: audio_h (B,N), prior_h (B,p,P) -> poses_h (B,F,P).
 
         The batch is cut into chunks; the host->device copy of chunk i+1, the kernels of chunk i and
@@ -172,6 +196,11 @@ class Engine:
         b = audio_h.shape[0]
         if not (audio_h.is_pinned() and prior_h.is_pinned() and poses_h.is_pinned()):
             raise RuntimeError("infer_host needs pinned host tensors (torch.Tensor.pin_memory())")
+        if self.batch_coupled and b > 0:
+            # Prior_MemoryEncoder multiplies by memory_encoding.t() @ pred_encoding, a sum over the clips of the call
+            # (Full_model/Models_memory.py:287-288): cutting the batch would change every clip's poses.  The whole
+            # batch goes through as ONE forward — same result as forward() on it — and only the copies are chunked.
+            return self._infer_host_whole(audio_h, prior_h, poses_h, mode, preemph, poses_dev)
         st = getattr(self, "_pipe", None)
         if st is None or st["chunk"] < min(chunk, b):
             c = min(chunk, b)
@@ -225,7 +254,17 @@ class Engine:
         main.wait_stream(st["d2h"])
         return poses_h
 
-    def capture(self, n_clips: int, mode: int = LOGMEL_LOG_IN, preemph: bool = True, with_emotion: bool = False):
+    def _infer_host_whole(self, audio_h, prior_h, poses_h, mode, preemph, poses_dev):
+        dev = self.device
+        audio = audio_h.to(dev, non_blocking=True)
+        prior = prior_h.to(dev, non_blocking=True)
+        poses = self.generator_forward(self.logmel(audio, mode, preemph), prior)[0]
+        if poses_dev is not None:
+            poses_dev.copy_(poses, non_blocking=True)
+        poses_h.copy_(poses, non_blocking=True)
+        return poses_h
+
+    def capture(self, n_clips: int, mode: int = LOGMEL_REFERENCE, preemph: bool = False, with_emotion: bool = False):
         """CUDA-graph the whole path (log-mel + generator forward, ~130 launches) for a fixed batch size.
 
         Small batches are launch-bound: a 1-clip forward is ~130 kernels of a few microseconds each.  The returned

@@ -14,7 +14,9 @@ small PyTorch module that keeps the tuple intact.
 """
 from __future__ import annotations
 
+import threading
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -22,6 +24,61 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .config import GeneratorConfig
+
+
+class EngineSet:
+    """The libegx engines of ONE generator, one per (CUDA device, precision).
+
+    nn.DataParallel (test_emotion_gesture_diversity_iterative.py:137-138) rebuilds its replicas on every call as
+    shallow `__dict__` copies of the wrapped module (torch.nn.Module._replicate_for_data_parallel) and runs them in
+    one Python thread per device.  This object sits in that `__dict__`, so the original module and every replica
+    share it by reference: a replica looks its engine up by the device of the inputs it was handed, the first call
+    on a device packs the weights there (from the ORIGINAL module — replicas own no parameters), later calls reuse
+    the handle.  libegx keeps no global state, so the per-device handles run concurrently."""
+
+    def __init__(self, source, cfg):
+        self._source = weakref.ref(source) if source is not None else None
+        self.cfg = cfg
+        self.engines = {}
+        self.lock = threading.Lock()
+
+    def __reduce__(self):            # pickling / deepcopy of the module: handles are per process, start empty
+        return (EngineSet, (None, self.cfg))
+
+    def bind(self, source):
+        if self._source is None or self._source() is None:
+            self._source = weakref.ref(source)
+
+    def source(self):
+        src = self._source() if self._source is not None else None
+        if src is None:
+            raise RuntimeError("the module these engines were packed from is gone")
+        return src
+
+    def get(self, device, precision="tc"):
+        from .engine import Engine
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("emotiongestures_b200 runs on sm_100a CUDA devices only (no CPU fallback); the generator "
+                               f"and its inputs are on {device}")
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, precision)
+        eng = self.engines.get(key)
+        if eng is None:
+            with self.lock:
+                eng = self.engines.get(key)
+                if eng is None:
+                    eng = Engine(self.cfg, torch.device("cuda", index), precision=precision)
+                    eng.load_state_dict(self.source().state_dict())
+                    self.engines[key] = eng
+        return eng
+
+    def sync(self):
+        """Re-pack every live engine from the source module's current weights."""
+        with self.lock:
+            sd = self.source().state_dict() if self.engines else None
+            for eng in self.engines.values():
+                eng.load_state_dict(sd)
 
 
 def _sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
@@ -326,7 +383,7 @@ class Transformer(nn.Module):
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
-        self._egx = None
+        self._egx_set = EngineSet(self, self.cfg)
 
     @classmethod
     def from_config(cls, cfg: GeneratorConfig, dropout=0.1):
@@ -348,19 +405,19 @@ class Transformer(nn.Module):
                    n_audio=cfg.n_audio)
 
     # -- engine plumbing -------------------------------------------------
-    def engine(self, precision="tc"):
-        """The libegx engine bound to this module's current weights/device."""
-        from .engine import Engine
-        dev = next(self.parameters()).device
-        if self._egx is None or self._egx.device != dev or self._egx.precision != precision:
-            self._egx = Engine(self.cfg, dev, precision=precision)
-            self._egx.load_state_dict(self.state_dict())
-        return self._egx
+    def engine(self, precision="tc", device=None):
+        """The libegx engine holding this module's weights on `device` (default: where the parameters live).
+        nn.DataParallel replicas own no parameters and pass the device of their inputs."""
+        if not getattr(self, "_is_replica", False):
+            self._egx_set.bind(self)
+        if device is None:
+            device = next(self.parameters()).device
+        return self._egx_set.get(device, precision)
 
     def sync_weights(self):
-        """Re-pack weights after `load_state_dict` / `.to()` (SURVEY.md §5 checkpoint row)."""
-        if self._egx is not None:
-            self._egx.load_state_dict(self.state_dict())
+        """Re-pack weights after `load_state_dict` / in-place edits (SURVEY.md §5 checkpoint row)."""
+        self._egx_set.bind(self)
+        self._egx_set.sync()
 
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
@@ -374,19 +431,29 @@ class Transformer(nn.Module):
             raise RuntimeError(
                 "emotiongestures_b200.Transformer is the inference path "
                 "(the reference released no generator training code); call .eval() first")
-        eng = self.engine(getattr(self, "precision", "tc"))
+        eng = self.engine(getattr(self, "precision", "tc"), _call_device(self, input_spectrum))
         text_embedding = self.text_encoder(text)
         poses, emo, sem, logits = eng.generator_forward(
             input_spectrum, prior_seq, sampled_emotion_feature)
         return poses, emo, sem, logits, text_embedding
 
     def forward_audio(self, audio, text, prior_seq, sampled_emotion_feature=None, *,
-                      mode=None, preemph=True):
-        """Raw 16 kHz audio (B,N) -> log-mel on the GPU -> forward (F1–F4 + generator)."""
-        from .config import LOGMEL_LOG_IN
-        eng = self.engine(getattr(self, "precision", "tc"))
-        spec = eng.logmel(audio, LOGMEL_LOG_IN if mode is None else mode, preemph)
+                      mode=None, preemph=False):
+        """Raw 16 kHz audio (B,N) -> log-mel on the GPU -> forward (F1–F4 + generator).  By default the features are
+        the ones the reference's checkpoints were trained on (config.LOGMEL_REFERENCE: no pre-emphasis, dB with
+        ref=max, fp16 storage rounding); pass `mode=LOGMEL_LOG_IN, preemph=True` for the ResNetSE34V2 recipe."""
+        from .config import LOGMEL_REFERENCE
+        eng = self.engine(getattr(self, "precision", "tc"), _call_device(self, audio))
+        spec = eng.logmel(audio, LOGMEL_REFERENCE if mode is None else mode, preemph)
         return self.forward(spec, text, prior_seq, sampled_emotion_feature)
+
+
+def _call_device(module, x):
+    """Device a forward call runs on: a DataParallel replica owns no parameters (they are plain attributes there), but
+    its inputs were scattered to its device; otherwise the module's own device."""
+    if getattr(module, "_is_replica", False) and isinstance(x, torch.Tensor) and x.is_cuda:
+        return x.device
+    return None
 
 
 class MemoryTransformer(Transformer):

@@ -1,7 +1,12 @@
 """Clip sharding across the GPUs of one box (one process per GPU, torch.distributed).
 
-Every clip is independent in eval mode (BatchNorm uses running statistics; InstanceNorm, SE,
-LayerNorm and attention are per clip), so the forward needs no collective.  Communication is
+With the plain generator (Full_model/Models.py) every clip is independent in eval mode (BatchNorm uses
+running statistics; InstanceNorm, SE, LayerNorm and attention are per clip), so the forward needs no
+collective and 1-GPU and N-GPU poses are bit-identical.  The Models_memory generator is the exception by
+construction of the reference: its temporal memory sums over the clips of one call
+(Full_model/Models_memory.py:287-288), so there a shard behaves like one nn.DataParallel replica of the
+reference — clips are coupled within a rank's shard, not across ranks — and results depend on the
+partition exactly as they do in the reference.  Communication is
 exactly the two steps BASELINE.json's north star names: the final pose gather and the FGD
 sufficient-statistics all-reduce (fgd.all_reduce_stats).  This replaces the reference's
 single-process nn.DataParallel scatter/replicate/gather per call

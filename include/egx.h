@@ -14,7 +14,10 @@
  *     which egx_set_weight copies
  *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); the
  *     library does not synchronise it (weight loading is the one exception)
- *   - no global state: one handle per device / per replica thread
+ *   - no mutable global state: one handle per device / per replica thread.  The only process-wide
+ *     values are read-only device properties (SM count, opt-in shared-memory sizes) cached by
+ *     egx_create; the library never reads the environment (the EGX_* variant / attribution
+ *     switches exist only in -DEGX_ATTRIBUTION builds)
  */
 #ifndef EGX_H
 #define EGX_H
@@ -55,12 +58,17 @@ typedef struct egx_cfg {
 } egx_cfg;
 
 enum { EGX_PREC_FP32 = 0,  /* CUDA-core fp32 everywhere (bit-faithful debugging arm)      */
-       EGX_PREC_TC   = 1   /* tcgen05: fp16 operands in the trunk, tf32 in the GEMM chain */ };
+       EGX_PREC_TC   = 1   /* tcgen05 kind::f16: fp16 operands, fp32 accumulation in TMEM, in the trunk
+                              convolutions, the Linear chain and the attention alike; fp32 residual
+                              stream, LayerNorm and outputs                                          */ };
 
 enum { EGX_DTYPE_F32 = 0, EGX_DTYPE_I64 = 1 };
 
 enum { EGX_LOGMEL_DB = 0,      /* utils/data_utils.py:36-37 (power_to_db, ref=max)          */
-       EGX_LOGMEL_LOG_IN = 1   /* model/ResNetSE34V2.py:96-98 (log(x+1e-6), InstanceNorm1d) */ };
+       EGX_LOGMEL_LOG_IN = 1,  /* model/ResNetSE34V2.py:96-98 (log(x+1e-6), InstanceNorm1d) */
+       /* OR-ed into EGX_LOGMEL_DB: round the result to fp16 and back, the astype('float16') storage cast of
+        * utils/data_utils.py:38 that every feature the reference's checkpoints saw went through */
+       EGX_LOGMEL_FP16_STORAGE = 0x100 };
 
 EGX_API int  egx_version(void);
 
@@ -82,6 +90,13 @@ EGX_API int  egx_finalize_weights(egx_handle* h);
  * (model/ResNetSE34V2.py:96-98).  audio (B,N) f32 -> out (B,128,n_cols) f32. */
 EGX_API int  egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols,
                 int mode, int preemph, float* out, void* stream);
+
+/* Replaces: make_audio_fixed_length (utils/data_utils.py:69-75) for a ragged batch.  Clip b is
+ * samples[offsets[b] .. offsets[b+1]) (f32 / int64, both device memory, n_clips + 1 offsets); every clip is cropped
+ * to n_out samples or extended at its end the way np.pad(mode='symmetric') does -> out (n_clips, n_out) f32, the
+ * `audio` argument of egx_logmel. */
+EGX_API int  egx_audio_fixed_length(egx_handle* h, const float* samples, const int64_t* offsets, int n_clips,
+                            int n_out, float* out, void* stream);
 
 /* Scratch the forward needs for a batch of n_clips (bytes). */
 EGX_API size_t egx_workspace_bytes(const egx_handle* h, int n_clips);

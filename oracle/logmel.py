@@ -1,10 +1,14 @@
 """ORACLE (test infrastructure, not product code): float64 log-mel front-end.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
-reference legs may import this.  PARITY UNPINNED for this stage: the reference
+reference legs may import this.  PARITY UNPINNED for F2-F4a: the reference
 computes these features offline with an un-vendored, un-versioned `librosa`
 (requirements.txt:5,16) and ships neither tests nor golden vectors for it, so
-this file restates the published algorithm from the reference's call sites:
+this file restates the published algorithm from the reference's call sites.
+F1, the F4b normalisation and F5 ARE pinned, against the real
+model.utils.PreEmphasis, torch.nn.InstanceNorm1d(128) and
+utils.data_utils.make_audio_fixed_length (oracle/make_golden_frontend.py ->
+tests/golden/frontend_pins.npz).
 
   F1  pre-emphasis            model/utils.py:22-38
   F2  STFT n_fft=1024 hop=512 utils/data_utils.py:36 (librosa.feature.melspectrogram, power=2)
@@ -36,8 +40,11 @@ def make_audio_fixed_length(audio: np.ndarray, n: int) -> np.ndarray:
 
 
 def preemphasis(x: np.ndarray, coef: float = 0.97) -> np.ndarray:
-    """model/utils.py:33-38: reflect-pad one sample on the left, then y[t] = x[t] - coef*x[t-1]."""
+    """model/utils.py:33-38: reflect-pad one sample on the left, then y[t] = x[t] - coef*x[t-1].  The module keeps
+    its filter as a torch.FloatTensor (:29-31), so the coefficient in force is float32(0.97) = 0.9700000286...
+    (pinned against the real module by oracle/make_golden_frontend.py)."""
     x = np.asarray(x, dtype=np.float64)
+    coef = float(np.float32(coef))
     prev = np.concatenate([x[..., 1:2], x[..., :-1]], axis=-1)
     return x - coef * prev
 

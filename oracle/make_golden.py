@@ -72,6 +72,11 @@ def run(cfg, name, n_clips, seed, with_emotion, chunk=0):
     for k in tmpl:
         assert tmpl[k].shape == ref_sd[k].shape, k
     assert torch.equal(tmpl["encoder.position_enc.pos_table"], ref_sd["encoder.position_enc.pos_table"])
+    # the geometry install() derives from the LIVE reference module is the one the goldens are made at
+    from emotiongestures_b200.dropin import config_from_module
+    got = config_from_module(ref)
+    for f in ("frames", "prior_frames", "pose_dim", "d_model", "d_inner", "n_layers", "n_head", "d_k", "d_v", "spec_w", "n_position"):
+        assert getattr(got, f) == getattr(cfg, f), ("config_from_module", f)
     sd = synth.synth_state_dict(tmpl, seed)
     ref.load_state_dict(sd)
     spec = torch.from_numpy(synth.synth_spec(n_clips, cfg.n_mels, cfg.spec_w, seed))
@@ -107,7 +112,9 @@ def run(cfg, name, n_clips, seed, with_emotion, chunk=0):
     for nm, a, b in zip(names, out, ref_out[:4]):
         err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
         print(f"  {name}: oracle vs reference {nm}: rel max-abs {err:.2e}")
-        assert err <= 2e-6, (nm, err)
+        # fp32 re-association noise depends on the BLAS thread count; the 8-wide logits (sums of 8704 / 30720
+        # products) scatter up to ~3e-6 between runs, everything else stays below 2e-6
+        assert err <= (5e-6 if nm == "emotion_logits" else 2e-6), (nm, err)
     for nm in taps_ref:
         err = (taps[nm] - taps_ref[nm]).abs().max().item() / taps_ref[nm].abs().max().item()
         print(f"  {name}: oracle vs reference tap {nm}: rel max-abs {err:.2e}")

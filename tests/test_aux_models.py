@@ -215,7 +215,7 @@ def test_evaluation_loop_matches_the_oracle_composition():
     skel, ssd = build(CASES["skeleton"][0], 23, *CASES["skeleton"][2])
     fgdn, fsd = build(mirrors.FGDNet, 24)
     ev = GestureEvaluator(gen.cuda(), vae.cuda(), skel.cuda(), fgdn.cuda(), n_pre_poses=BEAT.prior_frames)
-    ref_feats_p, ref_feats_t, ref = [], [], dict(acc=0.0, rot=0.0, l2=0.0)
+    ref_feats_p, ref_feats_t, ref = [], [], dict(acc=0.0, rot=0.0, l2=0.0, ambiguous=0)
     for it in range(2):
         n = 3
         spec = torch.from_numpy(synth.synth_spec(n, BEAT.n_mels, BEAT.spec_w, 40 + it))
@@ -233,6 +233,10 @@ def test_evaluation_loop_matches_the_oracle_composition():
             ref_feats_t.append(oa.fgd_latent(fsd, poses).reshape(-1, 512))
         assert rel_max(pred, o_pred) <= 3e-3
         ref["acc"] += 100.0 * (o_logits.argmax(1) == lab).double().mean().item()
+        # a clip's predicted class may legitimately differ only where the oracle's own top-2 margin is inside the
+        # classifier's 2e-3 parity tolerance
+        top2 = o_logits.topk(2, dim=1).values
+        ref["ambiguous"] += int(((top2[:, 0] - top2[:, 1]) <= 4e-3 * o_logits.abs().max()).sum())
         ref["rot"] += (poses.reshape(n, -1, 6) - o_pred.reshape(n, -1, 6)).abs().mean().item()
         ref["l2"] += (poses - o_pred).norm(dim=-1).mean().item()
     out = ev.finalize()
@@ -244,7 +248,7 @@ def test_evaluation_loop_matches_the_oracle_composition():
     assert np.allclose(mu_t, ft.mean(0), rtol=0, atol=3e-3 * np.abs(ft).max())
     assert abs(out["rotation_error_deg"] - ref["rot"] / 2 * 57.2958) <= 3e-3 * ref["rot"] / 2 * 57.2958
     assert abs(out["l2_pose"] - ref["l2"] / 2) <= 3e-3 * ref["l2"] / 2
-    assert abs(out["emotion_acc_percent"] - ref["acc"] / 2) <= 34.0          # one flipped argmax of 3 clips at most
+    assert abs(out["emotion_acc_percent"] - ref["acc"] / 2) <= 100.0 * ref["ambiguous"] / 6 + 1e-9
     want = fgd_mod.frechet_distance(fp.mean(0), np.cov(fp, rowvar=False), ft.mean(0), np.cov(ft, rowvar=False))
     assert np.isfinite(out["fgd"]) and abs(out["fgd"] - want) <= 2e-2 * max(abs(want), 1.0)
     assert abs(out["fgd"] - out["fgd_host"]) <= 1e-6 * max(abs(want), 1.0)      # device eigh tail == host numpy tail

@@ -47,6 +47,33 @@ def test_logmel_matches_fp64_oracle(cfg, mode, name, preemph, tol):
     assert err <= tol, f"log-mel max-abs {err:.3e} > {tol}"
 
 
+def test_frontend_matches_the_real_reference_pins():
+    """F1 + F4b + F5 of the CUDA path against tests/golden/frontend_pins.npz, which oracle/make_golden_frontend.py
+    made with the real model.utils.PreEmphasis, torch.nn.InstanceNorm1d(128) and make_audio_fixed_length."""
+    eng, _ = _engine("ted", 0, "fp32")
+    g = load_golden("frontend_pins")
+    audio = synth.synth_audio(3, 36267, seed=int(g["audio_seed"]))
+    got = eng.logmel(torch.from_numpy(audio), LOGMEL_LOG_IN, True, n_cols=70).cpu().double().numpy()
+    err = np.abs(got - g["log_in"]).max()
+    assert err <= 1e-4, f"log-mel (PreEmphasis + log + InstanceNorm1d) max-abs {err:.3e} vs the reference-made golden"
+    # F5: ragged clips -> fixed length, bit exact (it only moves samples)
+    lens = [int(n) for n in g["ragged_lens"]]
+    flat = torch.from_numpy(np.random.default_rng(int(g["ragged_seed"])).standard_normal(sum(lens)).astype(np.float32))
+    clips = list(torch.split(flat, lens))
+    fixed = eng.fixed_length_audio(clips, 36267).cpu().numpy()
+    assert fixed.shape == (len(lens), 36267)
+    assert np.array_equal(fixed[:, -64:], g["fixed_tail"])
+    assert np.array_equal(fixed.astype(np.float64).sum(axis=1), g["fixed_checksum"])
+    for c, row in zip(clips, fixed):
+        assert np.array_equal(row, ol.make_audio_fixed_length(c.numpy(), 36267))
+    # ragged clips straight into the features: same as padding on the host first
+    a = eng.logmel(eng.fixed_length_audio(clips[:3], 36267)).cpu()
+    b = eng.logmel(torch.from_numpy(np.stack([ol.make_audio_fixed_length(c.numpy(), 36267) for c in clips[:3]]))).cpu()
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="empty clip"):
+        eng.fixed_length_audio([torch.zeros(0)])
+
+
 def test_logmel_no_preemph_and_ragged_cols():
     eng, _ = _engine("ted", 0, "fp32")
     audio = synth.synth_audio(3, 5000, seed=9)          # 10 STFT frames, short clip
@@ -143,14 +170,84 @@ def test_module_forward_and_audio_entry():
     audio = torch.from_numpy(synth.synth_audio(2, TED.n_audio, seed=3))
     prior = torch.from_numpy(synth.synth_prior(2, TED.prior_frames, TED.pose_dim, 3))
     text = torch.zeros(2, 60, dtype=torch.int64, device="cuda")
+    # default: the reference's live features (no pre-emphasis, dB ref=max, fp16 storage rounding; utils/data_utils.py:35-38)
     out = m.forward_audio(audio.cuda(), text, prior.cuda()[:, :TED.prior_frames])
     assert len(out) == 5 and out[0].shape == (2, 34, 126) and out[4].shape == (2, 60, 512)
+    db = ol.logmel(audio.numpy(), TED.spec_w, "db", preemph=False)
+    got_spec = m.engine("fp32").logmel(audio.cuda()).cpu()
+    # the fp16 grid at |x| < 80 is 1/16 wide at most: the device value is the fp16 neighbour of the fp64 one up to a tie
+    assert torch.equal(got_spec, got_spec.half().float()) and float((got_spec.double() - torch.from_numpy(db)).abs().max()) <= 0.0625 / 2 + 1e-4
+    with torch.no_grad():
+        ref = og.generator_forward(sd, TED, got_spec, prior)[0]
+    assert rel_fro(out[0].cpu(), ref) <= 1e-4
+    # the north star's recipe is an explicit opt-in
+    out = m.forward_audio(audio.cuda(), text, prior.cuda(), mode=LOGMEL_LOG_IN, preemph=True)
     spec = torch.from_numpy(ol.logmel(audio.numpy(), TED.spec_w, "log_in")).float()
     with torch.no_grad():
         ref = og.generator_forward(sd, TED, spec, prior)[0]
     assert rel_fro(out[0].cpu(), ref) <= 1e-4
     with pytest.raises(RuntimeError):
         m.train()(spec.cuda(), text, prior.cuda())
+
+
+def test_install_swaps_the_forward_of_a_live_module_and_of_its_replicas():
+    """dropin.install() on a live generator module (here the mirror: the GPU box has no reference tree; the real
+    reference classes are covered on CPU in tests/test_host.py and in oracle/make_golden.py): same signature and
+    5-tuple, poses match the reference-made golden, DataParallel replicas run on their own device's engine, training
+    mode falls through to the module's own forward."""
+    from emotiongestures_b200 import MemoryTransformer, Transformer, install
+    from emotiongestures_b200.generator import EngineSet
+    g = load_golden("ted_b2")
+    _, sd = model_and_sd("ted", int(g["seed"]))
+    m = Transformer.from_config(TED)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    base = type(m)
+    eng = install(m, precision="fp32")
+    assert type(m) is not base and isinstance(m, base) and m.egx_engine is eng and isinstance(m._egx_set, EngineSet)
+    spec, prior, _ = inputs(TED, int(g["n_clips"]), int(g["seed"]))
+    text = torch.zeros(spec.shape[0], 60, dtype=torch.int64, device="cuda")
+    out = m(spec.cuda(), text, prior.cuda())
+    assert len(out) == 5 and rel_fro(out[0].cpu(), g["poses"]) <= TOL["fp32"]
+    # a replica (what nn.DataParallel builds per call) must use the class-level forward with ITSELF as `self`
+    rep = torch.nn.parallel.replicate(m, [0])[0]
+    assert rep._is_replica and rep._egx_set is m._egx_set
+    out_r = rep(spec.cuda(), text, prior.cuda())
+    assert torch.equal(out_r[0], out[0])
+    wrapped = torch.nn.DataParallel(m)
+    assert torch.equal(wrapped(spec.cuda(), text, prior.cuda())[0], out[0])
+    with pytest.raises(RuntimeError, match="already applied"):
+        install(wrapped)
+    # new checkpoint -> egx_sync() re-packs every live engine
+    sd2 = synth.synth_state_dict(m.state_dict(), 7)
+    base.load_state_dict(m, sd2)
+    m.egx_sync()
+    with torch.no_grad():
+        ref2 = og.generator_forward(sd2, TED, spec, prior)[0]
+    assert rel_fro(m(spec.cuda(), text, prior.cuda())[0].cpu(), ref2) <= TOL["fp32"]
+    with pytest.raises(RuntimeError, match="inference path"):        # the mirror's own forward, reached through base.forward
+        m.train()(spec.cuda(), text, prior.cuda())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_install_under_dataparallel_on_two_gpus():
+    """The evaluation script's multi-GPU path (test_emotion_gesture_diversity_iterative.py:137-138): nn.DataParallel
+    scatters the batch, every replica thread runs its half on ITS device's libegx handle, poses are gathered on
+    device 0 and equal the single-device result bit for bit (per-clip results do not depend on the batch)."""
+    from emotiongestures_b200 import Transformer, install
+    _, sd = model_and_sd("ted", 0)
+    m = Transformer.from_config(TED)
+    m.load_state_dict(sd)
+    m = m.cuda(0).eval()
+    install(m, precision="tc")
+    spec, prior, _ = inputs(TED, 10, 4)
+    text = torch.zeros(10, 60, dtype=torch.int64, device="cuda:0")
+    single = m(spec.cuda(0), text, prior.cuda(0))
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    multi = dp(spec.cuda(0), text, prior.cuda(0))
+    assert sorted(k[0] for k in m._egx_set.engines) == [0, 1]
+    for a, b in zip(multi[:4], single[:4]):
+        assert a.device.index == 0 and torch.equal(a, b)
 
 
 def test_fgd_statistics_match_numpy():
@@ -176,13 +273,31 @@ def test_infer_host_pipeline_matches_single_shot():
     audio = torch.from_numpy(synth.synth_audio(n, TED.n_audio, seed=5)).pin_memory()
     prior = torch.from_numpy(synth.synth_prior(n, TED.prior_frames, TED.pose_dim, 5)).pin_memory()
     poses_h = torch.empty(n, TED.frames, TED.pose_dim).pin_memory()
-    eng.infer_host(audio, prior, poses_h, chunk=8)
+    eng.infer_host(audio, prior, poses_h, chunk=8, mode=LOGMEL_LOG_IN, preemph=True)
     torch.cuda.synchronize()
-    ref = eng.generator_forward(eng.logmel(audio.cuda()), prior.cuda())[0].cpu()
+    ref = eng.generator_forward(eng.logmel(audio.cuda(), LOGMEL_LOG_IN, True), prior.cuda())[0].cpu()
     assert torch.equal(poses_h, ref)
-    eng.infer_host(audio, prior, poses_h, chunk=8)          # slots are reused across calls
+    eng.infer_host(audio, prior, poses_h, chunk=8, mode=LOGMEL_LOG_IN, preemph=True)          # slots are reused across calls
     torch.cuda.synchronize()
     assert torch.equal(poses_h, ref)
+
+
+def test_infer_host_keeps_the_batch_whole_for_the_memory_generator():
+    """Models_memory.Transformer couples the clips of one call (Models_memory.py:287-288): the chunked host entry must
+    not cut that batch — its poses equal forward() on the whole batch, not on chunks."""
+    eng, _ = _engine("tedmem", 5, "fp32")
+    assert eng.batch_coupled
+    n = 11
+    audio = torch.from_numpy(synth.synth_audio(n, TED.n_audio, seed=6)).pin_memory()
+    prior = torch.from_numpy(synth.synth_prior(n, TED.prior_frames, TED.pose_dim, 6)).pin_memory()
+    poses_h = torch.empty(n, TED.frames, TED.pose_dim).pin_memory()
+    eng.infer_host(audio, prior, poses_h, chunk=4)
+    torch.cuda.synchronize()
+    spec = eng.logmel(audio.cuda())
+    whole = eng.generator_forward(spec, prior.cuda())[0].cpu()
+    assert torch.equal(poses_h, whole)
+    chunked = torch.cat([eng.generator_forward(spec[i:i + 4], prior[i:i + 4].cuda())[0].cpu() for i in range(0, n, 4)])
+    assert not torch.equal(chunked, whole), "the temporal memory no longer couples the batch?"
 
 
 def test_full_size_batch_properties():
@@ -216,7 +331,7 @@ def test_full_size_batch_properties():
 def test_cuda_graph_replay_matches_eager(n):
     """Engine.capture: one cudaGraphLaunch for log-mel + forward at a fixed small batch == the eager launches."""
     eng, _ = _engine("ted", 0, "tc")
-    path = eng.capture(n)
+    path = eng.capture(n, LOGMEL_LOG_IN, True)
     for seed in (3, 4):
         audio = torch.from_numpy(synth.synth_audio(n, TED.n_audio, seed=seed)).cuda()
         prior = torch.from_numpy(synth.synth_prior(n, TED.prior_frames, TED.pose_dim, seed)).cuda()

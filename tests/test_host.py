@@ -124,3 +124,47 @@ def test_frechet_distance_device_variant_matches_the_host_tail():
     acc[0], acc[1:4], acc[4:] = 50, x.sum(0), (x.T @ x).reshape(-1)
     mu, sig = fgd.finalize_stats_device(acc, 3)
     assert torch.allclose(mu, x.mean(0)) and torch.allclose(sig, torch.from_numpy(np.cov(x.numpy(), rowvar=False)))
+
+
+def test_install_fails_loudly_on_cpu_and_leaves_the_module_untouched():
+    """No CPU fallback: install() on a CPU module raises and does not swap anything."""
+    from emotiongestures_b200.dropin import install
+    m = Transformer.from_config(TED).eval()
+    cls = type(m)
+    with pytest.raises(RuntimeError, match="sm_100a CUDA devices only"):
+        install(m)
+    assert type(m) is cls and "egx_engine" not in m.__dict__
+
+
+def test_engine_set_is_shared_with_dataparallel_replicas():
+    """nn.DataParallel replicas are shallow __dict__ copies (torch Module._replicate_for_data_parallel): they must see
+    the SAME per-device engine table as the original and pick their engine by the device of their inputs."""
+    from emotiongestures_b200.generator import EngineSet, _call_device
+    m = Transformer.from_config(TED).eval()
+    rep = m._replicate_for_data_parallel()
+    assert rep._egx_set is m._egx_set and isinstance(rep._egx_set, EngineSet)
+    assert rep._is_replica and _call_device(m, torch.zeros(1)) is None
+    assert type(rep).forward is type(m).forward          # class-level forward: `self` is the replica, not the original
+    import pickle
+    m2 = pickle.loads(pickle.dumps(m))                   # handles are per process: a copy starts with an empty table
+    assert m2._egx_set.engines == {} and m2._egx_set is not m._egx_set
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m._egx_set.get(torch.device("cpu"))
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/Full_model"), reason="needs the reference tree (build container)")
+def test_dropin_reads_the_geometry_of_the_real_reference_modules():
+    """config_from_module / install() on the REAL Full_model.Models.Transformer and Models_memory.Transformer
+    (CPU, build container only; the GPU box has no reference tree)."""
+    from emotiongestures_b200.dropin import config_from_module, install
+    from oracle.make_golden import load_reference
+    for cfg, chunk in ((TED, 0), (BEAT, 0), (TED, 4)):
+        ref = load_reference(cfg, chunk)
+        got = config_from_module(ref)
+        for f in ("frames", "prior_frames", "pose_dim", "d_model", "d_inner", "n_layers", "n_head", "d_k", "d_v", "spec_w",
+                  "n_position"):
+            assert getattr(got, f) == getattr(cfg, f), (chunk, f)
+        cls = type(ref)
+        with pytest.raises(RuntimeError, match="sm_100a CUDA devices only"):
+            install(torch.nn.DataParallel(ref) if chunk else ref)
+        assert type(ref) is cls

@@ -53,3 +53,22 @@ def test_fixed_length_audio():
     assert np.array_equal(ol.make_audio_fixed_length(a, 6), a[:6])
     padded = ol.make_audio_fixed_length(a, 13)
     assert len(padded) == 13 and np.array_equal(padded[10:], a[::-1][:3])
+
+
+def test_frontend_pins_from_the_real_reference(golden_dir):
+    """F1 / F4b / F5 against outputs of the real model.utils.PreEmphasis, torch.nn.InstanceNorm1d(128) and
+    utils.data_utils.make_audio_fixed_length (oracle/make_golden_frontend.py)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "frontend_pins.npz"))
+    audio = synth.synth_audio(3, 36267, seed=int(g["audio_seed"]))
+    y = ol.preemphasis(audio)
+    assert np.array_equal(y[:, :2048], g["preemph_head"])
+    assert np.allclose(y.sum(axis=1), g["preemph_sum"], rtol=0, atol=1e-12)
+    assert np.allclose(np.abs(y).sum(axis=1), g["preemph_abs_sum"], rtol=1e-15)
+    assert np.abs(ol.logmel(audio, 70, "log_in", preemph=True) - g["log_in"]).max() <= 1e-11
+    lens = g["ragged_lens"]
+    flat = np.random.default_rng(int(g["ragged_seed"])).standard_normal(int(lens.sum())).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    fixed = np.stack([ol.make_audio_fixed_length(flat[off[i]:off[i + 1]], 36267) for i in range(len(lens))])
+    assert np.array_equal(fixed[:, -64:], g["fixed_tail"])
+    assert np.array_equal(fixed.astype(np.float64).sum(axis=1), g["fixed_checksum"])
