@@ -65,6 +65,8 @@ PROTOTYPES = {
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "egx_skeleton_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int)]),
+    "egx_beat_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "egx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "egx_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "egx_launch_count": (C.c_int64, [C.c_void_p]),

@@ -1651,6 +1651,21 @@ int egx_pose_feature_dim(const egx_handle* h, int kind) {
     return w.ready ? w.n_out : 0;
 }
 
+int egx_beat_align(egx_handle* h, const float* poses, int n_clips, int n_frames, int pose_dim, int frame_lo, int frame_hi,
+                   int order, double sigma, double pose_fps, const double* onset_times, const int32_t* onset_offsets,
+                   double* scores, unsigned char* beat_mask, void* stream) {
+    if (!h) return 1;
+    if (n_clips == 0) return 0;
+    if (n_clips < 0 || !poses || !onset_times || !onset_offsets || !scores) EGX_FAIL(h, "null pointer argument");
+    if (n_frames < 2 || n_frames > 64) EGX_FAIL(h, "beat alignment supports 2..64 frames per clip");
+    if (pose_dim < 174) EGX_FAIL(h, "beat alignment reads pose columns 18:42 and 150:174 (BEAT skeleton); pose_dim is too small");
+    if (order < 1 || !(sigma > 0.0) || !(pose_fps > 0.0)) EGX_FAIL(h, "order >= 1, sigma > 0 and pose_fps > 0 required");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(h, launch_beat_align(poses, n_clips, n_frames, pose_dim, frame_lo, frame_hi, order, sigma, pose_fps, onset_times,
+                                onset_offsets, scores, beat_mask, s));
+    return 0;
+}
+
 size_t egx_row_features_workspace(const egx_handle* h, int64_t n_rows) {
     if (!h || !h->fgd_mlp.ready || n_rows <= 0) return 0;
     return (size_t)n_rows * h->fgd_mlp.lin.ldw * sizeof(__half) + 256;

@@ -324,6 +324,11 @@ template <class T>
 int launch_mem_temporal(const float* prior, const float* pred, int B, int p, int n_pred, int P, int C, const float* enc,
                         const float* S, T* out, int ldo, cudaStream_t s);
 
+// ---- k_beat.cu ((f)4: pose beats + GAHR of model/Beat_score_v2.py) ----
+int launch_beat_align(const float* poses, int B, int F, int P, int lo, int hi, int order, double sigma, double pose_fps,
+                      const double* onset_t, const int* onset_off, double* scores, unsigned char* beat_mask,
+                      cudaStream_t s);
+
 // ---- k_aux.cu ----
 int launch_cvae_mlp(const CvaeW& w, const float* x, const float* y, const float* noise, int noise_is_z, int64_t n,
                     float* out, float* mu, float* logvar, cudaStream_t s);

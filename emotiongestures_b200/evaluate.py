@@ -1,7 +1,6 @@
 """The evaluation loop of test_emotion_gesture_diversity_iterative.py:191-255 on the B200 path.
 
-One `GestureEvaluator.step` is one iteration of that loop without the dataset and the beat-alignment
-metric (librosa onset detection on the host):
+One `GestureEvaluator.step` is one iteration of that loop without the dataset:
 
     sampled = Emotion_VAE.sample(eid)                                   (:204)   egx_cvae3_sample
     pred_pose, _, _, _, _ = generator(in_spec, text, pre_pose, sampled) (:205)   egx_generator_forward
@@ -11,6 +10,7 @@ metric (librosa onset detection on the host):
     _, f = FGD(pred_pose); _, g = FGD(target_pose)                      (:226-229) egx_row_features
     feature rows -> mean / covariance                                   (:230-232, 251-254) egx_fgd_accumulate
     l2  += l2_distance_pose(target, pred)                               (:236)
+    BL  += alignmenter.calculate_align(onsets, load_pose(pred))         (:243-248) egx_beat_align (given the onsets)
 
 Nothing goes through the host inside the loop: the per-frame FGD features are reduced to the
 [n | sum | gram] float64 accumulator on the GPU instead of being copied into a numpy array, and
@@ -38,7 +38,7 @@ def compute_acc(input_label, out):
 
 class GestureEvaluator:
     def __init__(self, generator, emotion_vae, skeleton_classifier, fgd_net, n_pre_poses: int, feature_dim: int = 512,
-                 group=None):
+                 group=None, beat_sigma: float = 0.3, beat_order: int = 2, pose_fps: int = 15):
         self.generator, self.vae, self.classifier, self.fgd_net = generator, emotion_vae, skeleton_classifier, fgd_net
         self.group = group                      # process group of the clip shards (None: default group / single rank)
         self.n_pre = int(n_pre_poses)
@@ -48,16 +48,20 @@ class GestureEvaluator:
         self.acc_pred = _fgd.new_accumulator(self.dim, dev)
         self.acc_target = _fgd.new_accumulator(self.dim, dev)
         self.shift = None                       # provisional mean (first batch), keeps the f64 cancellation harmless
-        self.sums = torch.zeros(4, dtype=torch.float64, device=dev)   # steps, accuracy, rotation error, l2
+        self.sums = torch.zeros(6, dtype=torch.float64, device=dev)   # steps, accuracy, rotation error, l2, beat score, beat clips
+        self.beat_cfg = (beat_sigma, beat_order, pose_fps)              # alignment(0.3, 2), 15 fps (:185, args)
+        self._aligner = None
 
     def _engine(self):
         eng = getattr(self.generator, "egx_engine", None)        # a live reference module after install()
         return eng if eng is not None else self.generator.engine(getattr(self.generator, "precision", "tc"))
 
     @torch.no_grad()
-    def step(self, in_spec, in_text_padded, pose_seq, eid_onehot, z=None):
+    def step(self, in_spec, in_text_padded, pose_seq, eid_onehot, z=None, onsets=None):
         """One loop iteration; returns the predicted poses (B, F, P).  `z` (B, 32) is the sampler's Gaussian draw
-        (drawn with torch.randn when omitted, like the reference; pass it for reproducible / sharded runs)."""
+        (drawn with torch.randn when omitted, like the reference; pass it for reproducible / sharded runs).
+        `onsets`: per clip the (onset_raw, onset_bt, onset_bt_rms) frame arrays of alignment.load_audio; when given,
+        the beat-alignment score of every predicted clip is added on the device (:243-248)."""
         dev = self.device
         pose_seq = pose_seq.to(dev, torch.float32)
         pre_pose = pose_seq[:, :self.n_pre]
@@ -80,7 +84,15 @@ class GestureEvaluator:
                     dist.broadcast(self.shift, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                                    group=self.group)
             eng.fgd_accumulate(feat, acc_buf, self.shift)
-        self.sums += torch.stack([torch.ones((), dtype=torch.float64, device=dev), acc, rot.double(), l2.double()])
+        beat = torch.zeros(2, dtype=torch.float64, device=dev)
+        if onsets is not None:
+            if self._aligner is None:
+                from .beat import alignment
+                self._aligner = alignment(self.beat_cfg[0], self.beat_cfg[1], engine=eng)
+            fps = self.beat_cfg[2]
+            scores = self._aligner.score_batch(pred_pose, onsets, 0, int(pred_pose.shape[1] / fps), fps)   # t_start 0 (:187-188)
+            beat = torch.stack([scores.sum(), torch.tensor(float(b), dtype=torch.float64, device=dev)])
+        self.sums += torch.cat([torch.stack([torch.ones((), dtype=torch.float64, device=dev), acc, rot.double(), l2.double()]), beat])
         return pred_pose
 
     def _world(self):
@@ -99,12 +111,13 @@ class GestureEvaluator:
         _fgd.all_reduce_stats(self.acc_target, self.group)
         mu_p, sig_p = _fgd.finalize_stats(self.acc_pred, self.dim, self.shift)
         mu_t, sig_t = _fgd.finalize_stats(self.acc_target, self.dim, self.shift)
-        steps, acc, rot, l2 = (float(v) for v in self.sums.cpu())
+        steps, acc, rot, l2, beat_sum, beat_n = (float(v) for v in self.sums.cpu())
         # the Frechet tail stays on the device (float64 eigh); the host version is the cross-check in the tests
         fgd_dev = _fgd.frechet_distance_device(*_fgd.finalize_stats_device(self.acc_pred, self.dim, self.shift),
                                                *_fgd.finalize_stats_device(self.acc_target, self.dim, self.shift))
         return {"fgd": fgd_dev, "fgd_host": _fgd.frechet_distance(mu_p, sig_p, mu_t, sig_t), "emotion_acc_percent": acc / steps,
                 "rotation_error_deg": rot / steps * 57.2958, "l2_pose": l2 / steps,
+                "beat_score": beat_sum / beat_n if beat_n else None,
                 "pred_stats": (mu_p, sig_p), "target_stats": (mu_t, sig_t)}
 
 

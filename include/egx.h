@@ -179,6 +179,19 @@ EGX_API int  egx_skeleton_forward(egx_handle* h, const float* poses, int n_clips
                           float* logits, float* mid_feature, void* workspace, size_t workspace_bytes, void* stream);
 EGX_API int  egx_skeleton_dims(const egx_handle* h, int* n_frames, int* pose_dim, int* d_model, int* n_class);
 
+/* Replaces: alignment.load_pose + calculate_align of model/Beat_score_v2.py (:79-127, :177-214), called per generated
+ * clip at test_emotion_gesture_diversity_iterative.py:243-248.  poses (n, n_frames <= 64, pose_dim >= 174) f32.  The
+ * eight joint-group speed series are searched for strict local minima (`order` neighbours each side, clipped ends):
+ * the right-side groups inside frames [frame_lo, frame_hi) = [t_start*fps, t_end*fps), the left-side ones over the whole
+ * clip, as the reference does.  onset_times (f64, seconds) holds, back to back, the three onset lists of every clip —
+ * load_audio's (onset_raw, onset_bt, onset_bt_rms) after librosa.frames_to_time; list l of clip b is
+ * onset_times[onset_offsets[3b+l] .. onset_offsets[3b+l+1]) (int32, 3n+1 entries).  scores (n) f64 = the reference's
+ * avg_dis_all_b2a per clip (NaN where a list is empty: the reference raises ZeroDivisionError there).  beat_mask
+ * (nullable, (n, 8, n_frames) u8) marks the beat frames per group in load_pose's return order, window-relative. */
+EGX_API int  egx_beat_align(egx_handle* h, const float* poses, int n_clips, int n_frames, int pose_dim, int frame_lo,
+                    int frame_hi, int order, double sigma, double pose_fps, const double* onset_times,
+                    const int32_t* onset_offsets, double* scores, unsigned char* beat_mask, void* stream);
+
 /* Parity probe of the tcgen05 Linear kernel alone: out = [relu](A W^T + bias) + addend, A (M,K), W (N,K),
  * out (M,N) f32; operands are rounded to fp16 inside.  Synchronises the stream (test-only). */
 EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const float* bias,

@@ -224,7 +224,13 @@ def test_evaluation_loop_matches_the_oracle_composition():
         y = torch.nn.functional.one_hot(lab, 8).float()
         z = rnd((n, 32), 42 + it, 2)
         text = torch.zeros(n, 60, dtype=torch.int64)
-        pred = ev.step(spec, text, poses, y, z=z).cpu()
+        rng = np.random.default_rng(50 + it)
+        ons = [[np.sort(rng.choice(120, size=int(rng.integers(1, 8)), replace=False)) for _ in range(3)] for _ in range(n)]
+        pred = ev.step(spec, text, poses, y, z=z, onsets=ons).cpu()
+        # beat alignment (model/Beat_score_v2.py) of the clips the GPU path produced, against the oracle on those clips
+        from oracle import beat as ob
+        ref["beat"] = ref.get("beat", 0.0) + sum(
+            ob.calculate_align(ons[i], ob.load_pose(pred[i].numpy(), 0, BEAT.frames // 15, 15, 2), 0.3, 15) for i in range(n))
         with torch.no_grad():
             sampled = oa.cvae3_sample(vsd, y, z)
             o_pred = og.generator_forward(gsd, BEAT, spec, poses[:, :BEAT.prior_frames], sampled)[0]
@@ -249,6 +255,7 @@ def test_evaluation_loop_matches_the_oracle_composition():
     assert abs(out["rotation_error_deg"] - ref["rot"] / 2 * 57.2958) <= 3e-3 * ref["rot"] / 2 * 57.2958
     assert abs(out["l2_pose"] - ref["l2"] / 2) <= 3e-3 * ref["l2"] / 2
     assert abs(out["emotion_acc_percent"] - ref["acc"] / 2) <= 100.0 * ref["ambiguous"] / 6 + 1e-9
+    assert abs(out["beat_score"] - ref["beat"] / 6) <= 1e-12
     want = fgd_mod.frechet_distance(fp.mean(0), np.cov(fp, rowvar=False), ft.mean(0), np.cov(ft, rowvar=False))
     assert np.isfinite(out["fgd"]) and abs(out["fgd"] - want) <= 2e-2 * max(abs(want), 1.0)
     assert abs(out["fgd"] - out["fgd_host"]) <= 1e-6 * max(abs(want), 1.0)      # device eigh tail == host numpy tail
