@@ -219,7 +219,7 @@ def test_install_swaps_the_forward_of_a_live_module_and_of_its_replicas():
     with pytest.raises(RuntimeError, match="already applied"):
         install(wrapped)
     # new checkpoint -> egx_sync() re-packs every live engine
-    sd2 = synth.synth_state_dict(m.state_dict(), 7)
+    sd2 = synth.synth_state_dict(sd, 7)
     base.load_state_dict(m, sd2)
     m.egx_sync()
     with torch.no_grad():
