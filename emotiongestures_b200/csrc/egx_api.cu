@@ -1282,6 +1282,7 @@ int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
         delete h;
         return 4;
     }
+    if (cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete h; return 2; }
     h->H[0] = c.n_mels; h->W[0] = c.spec_w;
     for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
     if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
@@ -1300,6 +1301,7 @@ void egx_destroy(egx_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (auto& kv : h->aux_owned)
         for (void* p : kv.second) cudaFree(p);
+    if (h->fgd_scratch) cudaFree(h->fgd_scratch);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     delete h;
 }
@@ -1592,8 +1594,18 @@ int egx_fgd_accumulate(egx_handle* h, const float* feats, int64_t n_rows, int di
     if (!feats || !acc) EGX_FAIL(h, "null pointer argument");
     if (dim <= 0 || n_rows < 0) EGX_FAIL(h, "dim must be positive and n_rows non-negative");
     cudaStream_t s = (cudaStream_t)stream;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    int n_split = 1;
+    const size_t need = fgd_scratch_doubles(n_rows, dim, h->sms, &n_split);
+    if (need > h->fgd_scratch_n) {
+        // first use (or a larger problem): cudaFree waits for work still reading the old scratch
+        if (h->fgd_scratch) cudaFree(h->fgd_scratch);
+        h->fgd_scratch = nullptr; h->fgd_scratch_n = 0;
+        EGX_CHECK_CUDA(h, cudaMalloc(&h->fgd_scratch, need * sizeof(double)));
+        h->fgd_scratch_n = need;
+    }
     StageScope sc(h, 8);
-    LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, s));
+    LAUNCH(h, launch_fgd_accumulate(feats, n_rows, dim, shift, acc, h->fgd_scratch, n_split, s));
     return 0;
 }
 

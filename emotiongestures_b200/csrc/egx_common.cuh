@@ -183,6 +183,9 @@ struct egx_handle {
     egx::RowMlpW fgd_mlp;
     egx::EmotionNetW emo;
     egx::SkeletonW skel;
+    int sms = 0;                                       // multiprocessors of the device (read-only property)
+    double* fgd_scratch = nullptr;                     // partial Gram blocks of egx_fgd_accumulate, grown on demand
+    size_t fgd_scratch_n = 0;
     int64_t launches = 0;
     // per-launch CUDA-event profiling (egx_profile_enable / egx_profile_read)
     bool profiling = false;
@@ -313,8 +316,10 @@ int attn_tc_init_device();
 int launch_attention_tc(const __half* q, int ldq, int q_col0, const __half* kv, int ldkv, int k_col0, int v_col0,
                         int B, int L, int n_head, __half* out, int ldo, cudaStream_t s);
 
-int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc,
-                          cudaStream_t s);
+// two-phase, deterministic: partial Gram blocks per row slice into `scratch` (fgd_scratch_doubles), then a fixed-order sum
+size_t fgd_scratch_doubles(int64_t n, int D, int sms, int* n_split_out);
+int launch_fgd_accumulate(const float* feats, int64_t n, int D, const double* shift, double* acc, double* scratch,
+                          int n_split, cudaStream_t s);
 
 // ---- k_memory.cu (Prior_MemoryEncoder between pred_conv and post_header) ----
 int launch_mem_spatial(float* pred, int B, int n_pred, int P, int C, const float* enc, const float* tm_w, const float* tm_b,

@@ -266,6 +266,32 @@ def test_fgd_statistics_match_numpy():
         np.testing.assert_allclose(sigma, np.cov(x64, rowvar=False), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,d", [(1_200_000, 128), (200_000, 512), (5_000, 90)])
+def test_fgd_statistics_at_scale(n, d):
+    """BASELINE config 5 sizes (>= 1 M feature rows; D = 512 on the fp64 tensor pipe; a width that is no multiple of the
+    128-wide Gram block): rtol 1e-9 on Sigma against numpy float64 on the same rows, and bit-identical on a re-run (the
+    partial blocks are summed in a fixed order, no atomics)."""
+    from emotiongestures_b200.fgd import finalize_stats
+    eng, _ = _engine("ted", 0, "fp32")
+    g = torch.Generator(device="cuda").manual_seed(n + d)
+    x = torch.randn(n, d, generator=g, device="cuda") * (torch.rand(d, generator=g, device="cuda") * 1.5 + 0.5) \
+        + torch.rand(d, generator=g, device="cuda") * 2 - 1
+    shift = x[:512].double().mean(0)
+    accs = []
+    for _ in range(2):
+        acc = torch.zeros(1 + d + d * d, dtype=torch.float64, device="cuda")
+        half = n // 3
+        eng.fgd_accumulate(x[:half], acc, shift)              # two calls accumulate into the same buffer
+        eng.fgd_accumulate(x[half:], acc, shift)
+        accs.append(acc)
+    assert torch.equal(accs[0], accs[1]), "statistics are not deterministic"
+    mu, sigma = finalize_stats(accs[0].cpu(), d, shift.cpu())
+    x64 = x.double().cpu().numpy()
+    np.testing.assert_allclose(mu, x64.mean(0), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(sigma, np.cov(x64, rowvar=False), rtol=1e-9, atol=1e-11)
+    assert np.array_equal(sigma, sigma.T)
+
+
 def test_infer_host_pipeline_matches_single_shot():
     """Chunked, copy-overlapped end-to-end entry == one-shot device path, bit for bit per clip."""
     eng, _ = _engine("ted", 0, "tc")
