@@ -640,6 +640,22 @@ int linear_tc(egx_handle* h, const LinearW& w, const __half* A, int lda, int M, 
     return 0;
 }
 
+// out = LayerNorm(A W^T + b + residual) (Full_model/SubLayers.py:53-57, 80-82).  d_model == 256: residual add and
+// LayerNorm run in the GEMM's epilogue (one thread owns the whole row), `pre` is untouched; otherwise the GEMM writes
+// the pre-LayerNorm rows to `pre` and the warp-per-row kernel normalises them.
+int linear_ln_tc(egx_handle* h, const LinearW& w, const LNW& ln, const __half* A, int lda, int M, const float* residual,
+                 float* pre, float* out32, __half* out16, cudaStream_t s) {
+    if (w.out == 256) {
+        GemmEpi e;
+        e.bias = w.b; e.addend = residual; e.addend_ld = w.out; e.ln_g = ln.g; e.ln_b = ln.b;
+        LAUNCH(h, launch_gemm_tc(A, lda, w.w16, w.ldw, M, w.out, w.in, e, out32, w.out, out16, w.out, s));
+        return 0;
+    }
+    if (linear_tc(h, w, A, lda, M, pre, w.out, nullptr, 0, 0, residual, 0, s)) return 1;
+    LAUNCH(h, launch_layernorm(pre, ln, M, w.out, out32, out16, s));
+    return 0;
+}
+
 // Trunk on the tensor-core arm over caller-provided buffers: act[3] hold (B, H0, W0, 32) fp16 maps, `down` a
 // (B, H0/2, W0/2, 64) one; returns the buffer and geometry of stage `upto` (0 stem, 1.. layers).
 struct TrunkBufs {
@@ -764,11 +780,9 @@ int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const
         const bool last = l == c.n_layers - 1;
         if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, F, c.n_head, sl.o16, hk, s));
-        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, x32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, x32, sl.pre, y32, sl.x1_16, s)) return 1;
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
-        if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, last ? enc_out : x32, last ? sl.enc16 : sl.x16, s));
+        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, c.d_inner, R, y32, sl.pre, last ? enc_out : x32, last ? sl.enc16 : sl.x16, s)) return 1;
     }
     const float* dx32 = prior_feat;
     const __half* dx16 = sl.prior16;
@@ -780,13 +794,11 @@ int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const
         if (linear_tc(h, a.q, dx16, d, R, nullptr, 0, sl.qkv16, hk, 0, nullptr, 0, s)) return 1;
         if (linear_tc(h, a.kv, sl.enc16, d, R, nullptr, 0, kv, 2 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, hk, 0, kv, 2 * hk, 0, hk, B, F, c.n_head, sl.o16, hk, s));
-        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, dx32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, dx32, sl.pre, y32, sl.x1_16, s)) return 1;
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
-        if (linear_tc(h, f.w2, sl.hid16, c.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
         float* o32 = last ? dec_out : x32;
         __half* o16 = last ? sl.dec16 : sl.x16;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, o32, o16, s));
+        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, c.d_inner, R, y32, sl.pre, o32, o16, s)) return 1;
         dx32 = o32; dx16 = o16;
     }
     StageScope sc5b(h, 5);
@@ -1535,6 +1547,25 @@ int egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, const flo
     return 0;
 }
 
+int egx_debug_linear_ln_tc(egx_handle* h, const float* A, const float* W, const float* bias, const float* residual,
+                           const float* ln_g, const float* ln_b, int M, int K, float* out32, void* out16, void* stream) {
+    if (!h || !A || !W || !ln_g || !ln_b || !out32) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    const int N = 256, ldk = (K + 7) / 8 * 8;
+    __half *a16 = nullptr, *w16 = nullptr;
+    EGX_CHECK_CUDA(h, cudaMalloc(&a16, (size_t)M * ldk * 2));
+    EGX_CHECK_CUDA(h, cudaMalloc(&w16, (size_t)N * ldk * 2));
+    LAUNCH(h, launch_cvt_pad_f16(A, M, K, K, a16, ldk, s));
+    LAUNCH(h, launch_cvt_pad_f16(W, N, K, K, w16, ldk, s));
+    GemmEpi e;
+    e.bias = bias; e.addend = residual; e.addend_ld = N; e.ln_g = ln_g; e.ln_b = ln_b;
+    LAUNCH(h, launch_gemm_tc(a16, ldk, w16, ldk, M, N, K, e, out32, N, static_cast<__half*>(out16), N, s));
+    EGX_CHECK_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(a16); cudaFree(w16);
+    return 0;
+}
+
 int egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int cin, const void* w16, int cout,
                       int ks, int stride, int relu_first, const float* bias, const float* scale,
                       const float* shift, void* out16, int nchw, float* se_part, void* stream) {
@@ -1783,11 +1814,9 @@ int egx_skeleton_forward(egx_handle* h, const float* poses, int n_clips, int n_f
         const FFNW& f = k.ffn[l];
         if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, k.T, k.n_head, sl.o16, hk, s));
-        if (linear_tc(h, a.fc, sl.o16, hk, R, sl.pre, d, nullptr, 0, 0, x32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, a.ln, R, d, y32, sl.x1_16, s));
+        if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, x32, sl.pre, y32, sl.x1_16, s)) return 1;
         if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, k.d_inner, 1, nullptr, 0, s)) return 1;
-        if (linear_tc(h, f.w2, sl.hid16, k.d_inner, R, sl.pre, d, nullptr, 0, 0, y32, 0, s)) return 1;
-        LAUNCH(h, launch_layernorm(sl.pre, f.ln, R, d, x32, sl.x16, s));
+        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, k.d_inner, R, y32, sl.pre, x32, sl.x16, s)) return 1;
     }
     if (mid_feature) EGX_CHECK_CUDA(h, cudaMemcpyAsync(mid_feature, x32, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // enc_output.reshape(B, -1) -> post_projector (:277-281): rows of x16 are already (clip, frame)-major

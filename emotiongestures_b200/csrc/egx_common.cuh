@@ -269,6 +269,9 @@ struct GemmEpi {
     const float* addend = nullptr;    // added after bias/relu; row index = row % addend_rows
     int addend_rows = 0;              // 0: row index = row
     int addend_ld = 0;
+    // tensor-core arm only: LayerNorm (eps 1e-6) of the finished row in the epilogue when N == 256 (launch_gemm_tc_ln_ok)
+    const float* ln_g = nullptr;
+    const float* ln_b = nullptr;
 };
 // C[M][N] (ldc) = A[M][K] (lda) * W[N][K]^T  (+ epilogue), fp32 CUDA cores
 int launch_gemm_f32(const float* A, int lda, const float* Wt, int M, int N, int K, float* C,

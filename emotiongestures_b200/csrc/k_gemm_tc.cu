@@ -90,13 +90,42 @@ struct GemmTcEpi {
     int relu;
     float* out32; int ld32;
     __half* out16; int ld16;
+    const float* ln_g;   // LN variant: LayerNorm weight / bias [N]; the epilogue writes LayerNorm(acc + bias + addend)
+    const float* ln_b;
     int debug;        // EGX_GEMM_DEBUG (attribution experiments only, wrong results): 1 = no global stores, 2 = no epilogue
     int tma16;        // fp16 output through shared-memory slabs + TMA stores (tmC) instead of per-thread stores
 };
 
 __device__ __forceinline__ void gemm_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int BN, bool RES>
+// 32 columns of one output row: fp32 and / or fp16 copies with 256-bit stores (ld32 % 8 == 0, ld16 % 16 == 0, 32-byte
+// aligned bases: what the LN variant requires of its callers)
+__device__ __forceinline__ void store_chunk32(const float (&v)[32], float* o32, __half* o16) {
+    if (o32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o32 + 8 * j), "f"(v[8 * j]),
+                         "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]),
+                         "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
+                         : "memory");
+    }
+    if (o16) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t u[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const __half2 h2 = __floats2half2_rn(v[16 * j + 2 * e], v[16 * j + 2 * e + 1]);
+                u[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o16 + 16 * j), "r"(u[0]), "r"(u[1]),
+                         "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                         : "memory");
+        }
+    }
+}
+
+template <int BN, bool RES, bool LN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmTcEpi ep) {
@@ -186,6 +215,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grp = (warp - 2) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        if constexpr (LN) {
+            // Residual + LayerNorm in the epilogue (Full_model/SubLayers.py:55-57,80-82: x = LN(dropout(fc(.)) + residual),
+            // eps 1e-6): N == BN == d_model, so this thread's accumulator row IS the whole LayerNorm row.  Pass 1 adds
+            // bias and residual, writes the sums back to TMEM and accumulates the moments about the row's first value
+            // (no cancellation however far the mean is from zero); pass 2 re-reads TMEM, normalises and stores.  The
+            // pre-LayerNorm tensor never exists in HBM and the separate layernorm launch is gone.
+            for (uint32_t tcount = grp; (int)tcount < walk.count; tcount += 2) {
+                int m0, n0;
+                gemm_tile<BN, RES>(walk, (int)tcount, &m0, &n0);
+                const int m = m0 + row;
+                const bool live = m < M;
+                const float* add_row = (ep.addend && live) ? ep.addend + (size_t)m * ep.addend_ld : nullptr;
+                float4 ad_n[8];
+                if (add_row) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row) + j4);
+                }
+                mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + grp * BN + ((uint32_t)(q * 32) << 16);
+                float v0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + c * 32, v);
+                    if (ep.bias) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bi = __ldg(reinterpret_cast<const float4*>(ep.bias + c * 32) + j4);
+                            v[4 * j4] += bi.x; v[4 * j4 + 1] += bi.y; v[4 * j4 + 2] += bi.z; v[4 * j4 + 3] += bi.w;
+                        }
+                    }
+                    if (add_row) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            v[4 * j4] += ad_n[j4].x; v[4 * j4 + 1] += ad_n[j4].y; v[4 * j4 + 2] += ad_n[j4].z; v[4 * j4 + 3] += ad_n[j4].w;
+                        }
+                        if (c + 1 < BN / 32) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + (c + 1) * 32) + j4);
+                        }
+                    }
+                    if (c == 0) v0 = v[0];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const float d = v[j] - v0; s1 += d; s2 = fmaf(d, d, s2); }
+                    tmem_st32(taddr + c * 32, v);
+                }
+                tmem_st_wait();
+                const float mean_d = s1 * (1.f / BN);
+                const float rstd = rsqrtf(fmaxf(s2 * (1.f / BN) - mean_d * mean_d, 0.f) + 1e-6f);
+                const float mean = v0 + mean_d;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_g + c * 32) + j4);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.ln_b + c * 32) + j4);
+                        v[4 * j4] = fmaf((v[4 * j4] - mean) * rstd, g4.x, b4.x);
+                        v[4 * j4 + 1] = fmaf((v[4 * j4 + 1] - mean) * rstd, g4.y, b4.y);
+                        v[4 * j4 + 2] = fmaf((v[4 * j4 + 2] - mean) * rstd, g4.z, b4.z);
+                        v[4 * j4 + 3] = fmaf((v[4 * j4 + 3] - mean) * rstd, g4.w, b4.w);
+                    }
+                    if (live)
+                        store_chunk32(v, ep.out32 ? ep.out32 + (size_t)m * ep.ld32 + c * 32 : nullptr,
+                                      ep.out16 ? ep.out16 + (size_t)m * ep.ld16 + c * 32 : nullptr);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[grp]);
+            }
+        } else {
         const bool relu = ep.relu != 0;
         const bool add_vec = (ep.addend_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.addend) & 15) == 0;
         // TMA-store path: this thread's row of the group's slabs, 16-byte chunks XOR-swizzled like SWIZZLE_64B
@@ -363,6 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tmem_empty[grp]);
         }
         if (ep.tma16 && row == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -385,7 +490,7 @@ int g_gemm_tma_store = 0;   // EGX_GEMM_TMA_STORE=1: fp16 outputs through shared
 int g_gemm_debug = 0;
 int g_gemm_res = 1;      // EGX_GEMM_RES=0 (attribution experiments only): never keep the weight slice resident
 
-template <int BN, bool RES>
+template <int BN, bool RES, bool LN = false>
 int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmTcEpi& ep,
               cudaStream_t s) {
     CUtensorMap ta, tb, tc_;
@@ -409,7 +514,8 @@ int launch_bn(const __half* A, int lda, const __half* W, int ldw, int M, int N, 
         const uint32_t bC[2] = {32, GM};
         if (!make_tmap_f16(&tc_, ep.out16, 2, dC, sC, bC, nullptr, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
     }
-    gemm_tc_kernel<BN, RES><<<grid, kGemmThreads, GemmCfg<BN, RES>::total(num_kb, e2.tma16 != 0), s>>>(ta, tb, tc_, M, N, K, e2);
+    if (LN) e2.tma16 = 0;
+    gemm_tc_kernel<BN, RES, LN><<<grid, kGemmThreads, GemmCfg<BN, RES>::total(num_kb, e2.tma16 != 0), s>>>(ta, tb, tc_, M, N, K, e2);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -428,6 +534,7 @@ int gemm_tc_init_device() {
     if (cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_max) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -442,7 +549,16 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 // A: [M][K] fp16 with row pitch lda (elements, multiple of 8); W: [N][K] fp16 with row pitch ldw.
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s) {
-    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16, g_gemm_debug, 0};
+    GemmTcEpi ep{e.bias, e.addend, e.addend_rows, e.addend_ld, e.relu, out32, ld32, out16, ld16, e.ln_g, e.ln_b, g_gemm_debug, 0};
+    if (e.ln_g) {
+        // LayerNorm epilogue: the tile must span the whole row (N == 256) and take the vector paths
+        const auto al32 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 31) == 0; };
+        if (N != 256 || !e.ln_b || e.relu || e.addend_rows != 0 || (e.addend && ((e.addend_ld & 3) || !al32(e.addend))) ||
+            (e.bias && !al32(e.bias)) || !al32(e.ln_g) || !al32(e.ln_b) || (out32 && ((ld32 & 7) || !al32(out32))) ||
+            (out16 && ((ld16 & 15) || !al32(out16))))
+            return -1;
+        return launch_bn<256, false, true>(A, lda, W, ldw, M, N, K, ep, s);
+    }
     const int num_kb = (K + GK - 1) / GK;
     const int m_tiles = (M + GM - 1) / GM;
     // weights resident when the slice fits and every CTA gets several m-tiles to amortise loading it

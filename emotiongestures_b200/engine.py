@@ -316,6 +316,21 @@ class Engine:
                                                      self._stream()), "egx_debug_linear_tc")
         return out
 
+    def debug_linear_ln_tc(self, a, w, bias, residual, ln_g, ln_b):
+        """LayerNorm(a @ w.T + bias + residual) through the LN-epilogue GEMM (w: (256, K)); returns (f32, f16) outputs."""
+        a, w = self._f32(a, "A"), self._f32(w, "W")
+        m, k = a.shape
+        bias = None if bias is None else self._f32(bias, "bias")
+        residual = None if residual is None else self._f32(residual, "residual")
+        ln_g, ln_b = self._f32(ln_g, "ln_g"), self._f32(ln_b, "ln_b")
+        out = torch.empty((m, 256), dtype=torch.float32, device=self.device)
+        out16 = torch.empty((m, 256), dtype=torch.float16, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_debug_linear_ln_tc(self._h, _ptr(a), _ptr(w), _ptr(bias), _ptr(residual), _ptr(ln_g),
+                                                        _ptr(ln_b), m, k, _ptr(out), _ptr(out16), self._stream()),
+                        "egx_debug_linear_ln_tc")
+        return out, out16
+
     def debug_conv_tc(self, x, w, scale, shift, bias=None, stride=1, relu_first=False, nchw=False,
                       se_sums=False):
         """x (B,Cin,H,W) f32, w (Cout,Cin,ks,ks) f32 -> (B,Cout,Ho,Wo) f32 via the tcgen05 conv kernel."""

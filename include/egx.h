@@ -198,6 +198,13 @@ EGX_API int  egx_debug_linear_tc(egx_handle* h, const float* A, const float* W, 
                          const float* addend, int addend_rows, int M, int N, int K, int relu,
                          float* out32, void* stream);
 
+/* Parity probe of the Linear + residual + LayerNorm epilogue variant (N = 256): out = LayerNorm(A W^T + bias + residual)
+ * * ln_g + ln_b, eps 1e-6 (Full_model/SubLayers.py:53-57,80-82); out32 (M,256) f32 and, when not NULL, out16 (M,256)
+ * f16.  Synchronises the stream (test-only). */
+EGX_API int  egx_debug_linear_ln_tc(egx_handle* h, const float* A, const float* W, const float* bias,
+                            const float* residual, const float* ln_g, const float* ln_b, int M, int K,
+                            float* out32, void* out16, void* stream);
+
 /* Parity probe of the tcgen05 implicit-GEMM convolution alone.  in16: NHWC fp16 (B,H,W,cin); w16: fp16
  * [cout][ks*ks][cin]; y = (relu_first ? relu(acc+bias) : acc+bias)*scale + shift; out16: NHWC fp16, or
  * (B,cout,Ho*Wo) fp16 when nchw != 0; se_part (nullable): [B][tiles][cout] per-tile channel sums. */

@@ -38,6 +38,25 @@ def test_linear_tc(eng, m, n, k, epi):
     assert rel_max(got, ref) <= 2e-5
 
 
+@pytest.mark.parametrize("m,k", [(34, 512), (300, 1024), (5000, 512), (40000, 1024), (129, 256)])
+@pytest.mark.parametrize("offset", [0.0, 50.0])
+def test_linear_residual_layernorm_epilogue(eng, m, k, offset):
+    """LayerNorm(A W^T + b + residual) computed in the GEMM epilogue (one thread owns the 256-wide row) against
+    float64 on the fp16-rounded operands; `offset` puts the row mean 50 standard deviations from zero (the moments
+    are taken about the row's first value, so nothing cancels)."""
+    g = torch.Generator().manual_seed(m + k)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(256, k, generator=g) / k ** 0.5
+    bias = torch.randn(256, generator=g) * 0.1
+    res = torch.randn(m, 256, generator=g) + offset
+    ln_g, ln_b = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    got32, got16 = eng.debug_linear_ln_tc(a, w, bias, res, ln_g, ln_b)
+    pre = a.half().double() @ w.half().double().t() + bias.double() + res.double()
+    ref = torch.nn.functional.layer_norm(pre, (256,), ln_g.double(), ln_b.double(), eps=1e-6)
+    assert rel_max(got32.cpu(), ref) <= (2e-5 if offset == 0 else 2e-4)
+    assert torch.equal(got16.cpu(), got32.cpu().half())
+
+
 @pytest.mark.parametrize("cin,cout,h,w,ks,stride,nchw", [
     (32, 32, 128, 70, 3, 1, False), (64, 64, 64, 35, 3, 1, False), (128, 128, 32, 18, 3, 1, False),
     (128, 34, 32, 18, 3, 1, True), (128, 60, 32, 31, 3, 1, True), (64, 64, 64, 62, 3, 1, False),
