@@ -44,6 +44,7 @@ PROTOTYPES = {
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "egx_debug_linear_ln_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "egx_debug_ffn_tc": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "egx_debug_conv_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -656,6 +656,21 @@ int linear_ln_tc(egx_handle* h, const LinearW& w, const LNW& ln, const __half* A
     return 0;
 }
 
+// PositionwiseFeedForward (Full_model/SubLayers.py:74-84): one fused kernel when the geometry allows (d_model = 256),
+// else w1 GEMM (+ReLU) -> hid16, w2 GEMM + residual + LayerNorm.  x16 / resid are the block input in fp16 / fp32.
+int ffn_block_tc(egx_handle* h, const FFNW& f, const __half* x16, const float* resid, int M, __half* hid16, float* pre,
+                 float* out32, __half* out16, cudaStream_t s) {
+    static const bool fused = env_switch("EGX_FFN_FUSED", 1) != 0;
+    const int d = f.w1.in, d_inner = f.w1.out;
+    if (fused && ffn_tc_supported(d, d_inner) && f.w1.b && f.w2.b) {
+        LAUNCH(h, launch_ffn_tc(x16, resid, f.w1.w16, f.w1.ldw, f.w1.b, f.w2.w16, f.w2.ldw, f.w2.b, f.ln.g, f.ln.b, M, d_inner,
+                                out32, out16, s));
+        return 0;
+    }
+    if (linear_tc(h, f.w1, x16, d, M, nullptr, 0, hid16, d_inner, 1, nullptr, 0, s)) return 1;
+    return linear_ln_tc(h, f.w2, f.ln, hid16, d_inner, M, resid, pre, out32, out16, s);
+}
+
 // Trunk on the tensor-core arm over caller-provided buffers: act[3] hold (B, H0, W0, 32) fp16 maps, `down` a
 // (B, H0/2, W0/2, 64) one; returns the buffer and geometry of stage `upto` (0 stem, 1.. layers).
 struct TrunkBufs {
@@ -781,8 +796,7 @@ int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const
         if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, F, c.n_head, sl.o16, hk, s));
         if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, x32, sl.pre, y32, sl.x1_16, s)) return 1;
-        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
-        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, c.d_inner, R, y32, sl.pre, last ? enc_out : x32, last ? sl.enc16 : sl.x16, s)) return 1;
+        if (ffn_block_tc(h, f, sl.x1_16, y32, R, sl.hid16, sl.pre, last ? enc_out : x32, last ? sl.enc16 : sl.x16, s)) return 1;
     }
     const float* dx32 = prior_feat;
     const __half* dx16 = sl.prior16;
@@ -795,10 +809,9 @@ int forward_tail_tc(egx_handle* h, TcSlots& sl, int B, const __half* fcin, const
         if (linear_tc(h, a.kv, sl.enc16, d, R, nullptr, 0, kv, 2 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, hk, 0, kv, 2 * hk, 0, hk, B, F, c.n_head, sl.o16, hk, s));
         if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, dx32, sl.pre, y32, sl.x1_16, s)) return 1;
-        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, c.d_inner, 1, nullptr, 0, s)) return 1;
         float* o32 = last ? dec_out : x32;
         __half* o16 = last ? sl.dec16 : sl.x16;
-        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, c.d_inner, R, y32, sl.pre, o32, o16, s)) return 1;
+        if (ffn_block_tc(h, f, sl.x1_16, y32, R, sl.hid16, sl.pre, o32, o16, s)) return 1;
         dx32 = o32; dx16 = o16;
     }
     StageScope sc5b(h, 5);
@@ -1298,7 +1311,7 @@ int egx_create(const egx_cfg* cfg, int device, egx_handle** out) {
     h->H[0] = c.n_mels; h->W[0] = c.spec_w;
     for (int i = 1; i < 3; ++i) { h->H[i] = (h->H[i - 1] + 1) / 2; h->W[i] = (h->W[i - 1] + 1) / 2; }
     if (!build_logmel_tables(h)) { egx_destroy(h); return 5; }
-    if (gemm_tc_init_device() != 0 || conv_tc_init_device() != 0 || attn_tc_init_device() != 0) {
+    if (gemm_tc_init_device() != 0 || conv_tc_init_device() != 0 || attn_tc_init_device() != 0 || ffn_tc_init_device() != 0) {
         egx_destroy(h);
         return 6;
     }
@@ -1566,6 +1579,25 @@ int egx_debug_linear_ln_tc(egx_handle* h, const float* A, const float* W, const 
     return 0;
 }
 
+int egx_debug_ffn_tc(egx_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* ln_g, const float* ln_b, int M, int d_inner, float* out32, void* out16, void* stream) {
+    if (!h || !x || !w1 || !b1 || !w2 || !b2 || !ln_g || !ln_b || !out32 || !out16) return 1;
+    if (!ffn_tc_supported(256, d_inner)) EGX_FAIL(h, "fused FFN needs d_model = 256 and d_inner a multiple of 256");
+    cudaStream_t s = (cudaStream_t)stream;
+    EGX_CHECK_CUDA(h, cudaSetDevice(h->device));
+    __half *x16 = nullptr, *w1h = nullptr, *w2h = nullptr;
+    EGX_CHECK_CUDA(h, cudaMalloc(&x16, (size_t)M * 256 * 2));
+    EGX_CHECK_CUDA(h, cudaMalloc(&w1h, (size_t)d_inner * 256 * 2));
+    EGX_CHECK_CUDA(h, cudaMalloc(&w2h, (size_t)256 * d_inner * 2));
+    LAUNCH(h, launch_cvt_pad_f16(x, M, 256, 256, x16, 256, s));
+    LAUNCH(h, launch_cvt_pad_f16(w1, d_inner, 256, 256, w1h, 256, s));
+    LAUNCH(h, launch_cvt_pad_f16(w2, 256, d_inner, d_inner, w2h, d_inner, s));
+    LAUNCH(h, launch_ffn_tc(x16, x, w1h, 256, b1, w2h, d_inner, b2, ln_g, ln_b, M, d_inner, out32, static_cast<__half*>(out16), s));
+    EGX_CHECK_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(x16); cudaFree(w1h); cudaFree(w2h);
+    return 0;
+}
+
 int egx_debug_conv_tc(egx_handle* h, const void* in16, int B, int H, int W, int cin, const void* w16, int cout,
                       int ks, int stride, int relu_first, const float* bias, const float* scale,
                       const float* shift, void* out16, int nchw, float* se_part, void* stream) {
@@ -1815,8 +1847,7 @@ int egx_skeleton_forward(egx_handle* h, const float* poses, int n_clips, int n_f
         if (linear_tc(h, a.qkv, sl.x16, d, R, nullptr, 0, sl.qkv16, 3 * hk, 0, nullptr, 0, s)) return 1;
         LAUNCH(h, launch_attention_tc(sl.qkv16, 3 * hk, 0, sl.qkv16, 3 * hk, hk, 2 * hk, B, k.T, k.n_head, sl.o16, hk, s));
         if (linear_ln_tc(h, a.fc, a.ln, sl.o16, hk, R, x32, sl.pre, y32, sl.x1_16, s)) return 1;
-        if (linear_tc(h, f.w1, sl.x1_16, d, R, nullptr, 0, sl.hid16, k.d_inner, 1, nullptr, 0, s)) return 1;
-        if (linear_ln_tc(h, f.w2, f.ln, sl.hid16, k.d_inner, R, y32, sl.pre, x32, sl.x16, s)) return 1;
+        if (ffn_block_tc(h, f, sl.x1_16, y32, R, sl.hid16, sl.pre, x32, sl.x16, s)) return 1;
     }
     if (mid_feature) EGX_CHECK_CUDA(h, cudaMemcpyAsync(mid_feature, x32, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // enc_output.reshape(B, -1) -> post_projector (:277-281): rows of x16 are already (clip, frame)-major

@@ -304,6 +304,13 @@ int launch_cvt_pad_f16(const float* in, int64_t rows, int cols, int ld_in, __hal
 int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpi& e,
                    float* out32, int ld32, __half* out16, int ld16, cudaStream_t s);
 
+// fused position-wise feed-forward block (k_ffn_tc.cu): LayerNorm(x + W2 relu(W1 x + b1) + b2), d_model = 256
+int ffn_tc_init_device();
+bool ffn_tc_supported(int d_model, int d_inner);
+int launch_ffn_tc(const __half* x16, const float* resid, const __half* w1, int ldw1, const float* b1, const __half* w2, int ldw2,
+                  const float* b2, const float* ln_g, const float* ln_b, int M, int d_inner, float* out32, __half* out16,
+                  cudaStream_t s);
+
 int conv_tc_init_device();
 // in: NHWC fp16 (B,Hin,Win,cin); out: NHWC fp16 or (B,cout,Ho*Wo) fp16 when nchw != 0
 // se_part (optional): [B][conv_tc_tiles_per_clip(Ho,Wo)][cout] per-tile channel sums (fixed order)

@@ -229,6 +229,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float* add_row = (ep.addend && live) ? ep.addend + (size_t)m * ep.addend_ld : nullptr;
                 float4 ad_n[8];
                 if (add_row) {
+                    // the rest of the residual row goes to L2 now, its first chunk to registers
+#pragma unroll
+                    for (int l = 1; l < BN / 32; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + l * 32));
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row) + j4);
                 }

@@ -331,6 +331,18 @@ class Engine:
                         "egx_debug_linear_ln_tc")
         return out, out16
 
+    def debug_ffn_tc(self, x, w1, b1, w2, b2, ln_g, ln_b):
+        """LayerNorm(x + relu(x @ w1.T + b1) @ w2.T + b2) through the fused feed-forward kernel; (f32, f16) outputs."""
+        x, w1, b1, w2, b2, ln_g, ln_b = (self._f32(t, "arg") for t in (x, w1, b1, w2, b2, ln_g, ln_b))
+        m, d_inner = x.shape[0], w1.shape[0]
+        out = torch.empty((m, 256), dtype=torch.float32, device=self.device)
+        out16 = torch.empty((m, 256), dtype=torch.float16, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_debug_ffn_tc(self._h, _ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(ln_g),
+                                                  _ptr(ln_b), m, d_inner, _ptr(out), _ptr(out16), self._stream()),
+                        "egx_debug_ffn_tc")
+        return out, out16
+
     def debug_conv_tc(self, x, w, scale, shift, bias=None, stride=1, relu_first=False, nchw=False,
                       se_sums=False):
         """x (B,Cin,H,W) f32, w (Cout,Cin,ks,ks) f32 -> (B,Cout,Ho,Wo) f32 via the tcgen05 conv kernel."""

@@ -205,6 +205,13 @@ EGX_API int  egx_debug_linear_ln_tc(egx_handle* h, const float* A, const float* 
                             const float* residual, const float* ln_g, const float* ln_b, int M, int K,
                             float* out32, void* out16, void* stream);
 
+/* Parity probe of the fused feed-forward kernel alone (Full_model/SubLayers.py:74-84, d_model = 256):
+ * out = LayerNorm(x + W2 relu(W1 x + b1) + b2); x (M,256), W1 (d_inner,256), W2 (256,d_inner) f32 (rounded to fp16 inside,
+ * the residual stays f32); out32 (M,256) f32, out16 (M,256) f16.  Synchronises the stream (test-only). */
+EGX_API int  egx_debug_ffn_tc(egx_handle* h, const float* x, const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* ln_g, const float* ln_b, int M, int d_inner, float* out32,
+                      void* out16, void* stream);
+
 /* Parity probe of the tcgen05 implicit-GEMM convolution alone.  in16: NHWC fp16 (B,H,W,cin); w16: fp16
  * [cout][ks*ks][cin]; y = (relu_first ? relu(acc+bias) : acc+bias)*scale + shift; out16: NHWC fp16, or
  * (B,cout,Ho*Wo) fp16 when nchw != 0; se_part (nullable): [B][tiles][cout] per-tile channel sums. */

@@ -57,6 +57,27 @@ def test_linear_residual_layernorm_epilogue(eng, m, k, offset):
     assert torch.equal(got16.cpu(), got32.cpu().half())
 
 
+@pytest.mark.parametrize("m,d_inner", [(34, 1024), (128, 1024), (129, 256), (1000, 512), (40000, 1024)])
+def test_fused_feed_forward_block(eng, m, d_inner):
+    """k_ffn_tc.cu: LayerNorm(x + W2 relu(W1 x + b1) + b2) in one kernel against float64 on the fp16-rounded operands;
+    the hidden activations are rounded to fp16 between the two GEMMs exactly as the unfused chain stores them."""
+    g = torch.Generator().manual_seed(m + d_inner)
+    x = torch.randn(m, 256, generator=g)
+    w1 = torch.randn(d_inner, 256, generator=g) / 16
+    b1 = torch.randn(d_inner, generator=g) * 0.1
+    w2 = torch.randn(256, d_inner, generator=g) / d_inner ** 0.5
+    b2 = torch.randn(256, generator=g) * 0.1
+    ln_g, ln_b = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    got32, got16 = eng.debug_ffn_tc(x, w1, b1, w2, b2, ln_g, ln_b)
+    hid = (x.half().double() @ w1.half().double().t() + b1.double()).clamp_min(0).float().half().double()
+    pre = hid @ w2.half().double().t() + b2.double() + x.double()
+    ref = torch.nn.functional.layer_norm(pre, (256,), ln_g.double(), ln_b.double(), eps=1e-6)
+    # the fp16 rounding of a hidden value can flip on an fp32-accumulation-order difference: one half-ulp of one
+    # of d_inner terms, far below the 2e-3 budget but above pure re-association noise
+    assert rel_max(got32.cpu(), ref) <= 1e-4
+    assert torch.equal(got16.cpu(), got32.cpu().half())
+
+
 @pytest.mark.parametrize("cin,cout,h,w,ks,stride,nchw", [
     (32, 32, 128, 70, 3, 1, False), (64, 64, 64, 35, 3, 1, False), (128, 128, 32, 18, 3, 1, False),
     (128, 34, 32, 18, 3, 1, True), (128, 60, 32, 31, 3, 1, True), (64, 64, 64, 62, 3, 1, False),
