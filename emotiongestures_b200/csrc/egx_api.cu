@@ -159,9 +159,15 @@ bool make_mha(egx_handle* h, const std::string& pre, const egx_cfg& c, MHAW* m) 
 }
 
 bool make_ffn(egx_handle* h, const std::string& pre, const egx_cfg& c, FFNW* f) {
-    return make_linear(h, pre + ".w_1", c.d_model, c.d_inner, true, &f->w1) &&
-           make_linear(h, pre + ".w_2", c.d_inner, c.d_model, true, &f->w2) &&
-           make_ln(h, pre + ".layer_norm", c.d_model, &f->ln);
+    if (!(make_linear(h, pre + ".w_1", c.d_model, c.d_inner, true, &f->w1) &&
+          make_linear(h, pre + ".w_2", c.d_inner, c.d_model, true, &f->w2) &&
+          make_ln(h, pre + ".layer_norm", c.d_model, &f->ln)))
+        return false;
+    f->h_b1 = find(h, pre + ".w_1.bias")->v;
+    f->h_b2 = find(h, pre + ".w_2.bias")->v;
+    f->h_g = find(h, pre + ".layer_norm.weight")->v;
+    f->h_b = find(h, pre + ".layer_norm.bias")->v;
+    return true;
 }
 
 // SE-ResNet trunk under `fe` (Full_model/ResNetSE34V2.py:13-55; model/emotion_ResNetSE34V2.py adds layer4):
@@ -662,9 +668,9 @@ int ffn_block_tc(egx_handle* h, const FFNW& f, const __half* x16, const float* r
                  float* out32, __half* out16, cudaStream_t s) {
     static const bool fused = env_switch("EGX_FFN_FUSED", 1) != 0;
     const int d = f.w1.in, d_inner = f.w1.out;
-    if (fused && ffn_tc_supported(d, d_inner) && f.w1.b && f.w2.b) {
-        LAUNCH(h, launch_ffn_tc(x16, resid, f.w1.w16, f.w1.ldw, f.w1.b, f.w2.w16, f.w2.ldw, f.w2.b, f.ln.g, f.ln.b, M, d_inner,
-                                out32, out16, s));
+    if (fused && ffn_tc_supported(d, d_inner) && (int)f.h_b1.size() == d_inner && (int)f.h_b2.size() == d) {
+        LAUNCH(h, launch_ffn_tc(x16, resid, f.w1.w16, f.w1.ldw, f.h_b1.data(), f.w2.w16, f.w2.ldw, f.h_b2.data(), f.h_g.data(),
+                                f.h_b.data(), M, d_inner, out32, out16, s));
         return 0;
     }
     if (linear_tc(h, f.w1, x16, d, M, nullptr, 0, hid16, d_inner, 1, nullptr, 0, s)) return 1;
@@ -1592,7 +1598,13 @@ int egx_debug_ffn_tc(egx_handle* h, const float* x, const float* w1, const float
     LAUNCH(h, launch_cvt_pad_f16(x, M, 256, 256, x16, 256, s));
     LAUNCH(h, launch_cvt_pad_f16(w1, d_inner, 256, 256, w1h, 256, s));
     LAUNCH(h, launch_cvt_pad_f16(w2, 256, d_inner, d_inner, w2h, d_inner, s));
-    LAUNCH(h, launch_ffn_tc(x16, x, w1h, 256, b1, w2h, d_inner, b2, ln_g, ln_b, M, d_inner, out32, static_cast<__half*>(out16), s));
+    std::vector<float> hb1(d_inner), hb2(256), hg(256), hb(256);
+    EGX_CHECK_CUDA(h, cudaMemcpy(hb1.data(), b1, sizeof(float) * d_inner, cudaMemcpyDeviceToHost));
+    EGX_CHECK_CUDA(h, cudaMemcpy(hb2.data(), b2, sizeof(float) * 256, cudaMemcpyDeviceToHost));
+    EGX_CHECK_CUDA(h, cudaMemcpy(hg.data(), ln_g, sizeof(float) * 256, cudaMemcpyDeviceToHost));
+    EGX_CHECK_CUDA(h, cudaMemcpy(hb.data(), ln_b, sizeof(float) * 256, cudaMemcpyDeviceToHost));
+    LAUNCH(h, launch_ffn_tc(x16, x, w1h, 256, hb1.data(), w2h, d_inner, hb2.data(), hg.data(), hb.data(), M, d_inner, out32,
+                            static_cast<__half*>(out16), s));
     EGX_CHECK_CUDA(h, cudaStreamSynchronize(s));
     cudaFree(x16); cudaFree(w1h); cudaFree(w2h);
     return 0;

@@ -61,7 +61,10 @@ struct BlockW {
 };
 
 struct MHAW { LinearW q, k, v, kv, qkv, fc; LNW ln; };
-struct FFNW { LinearW w1, w2; LNW ln; };
+struct FFNW {
+    LinearW w1, w2; LNW ln;
+    std::vector<float> h_b1, h_b2, h_g, h_b;      // host copies: the fused kernel takes them as kernel parameters
+};
 
 // (f)1  Full_model/Models_memory.py Prior_MemoryEncoder (the prior encoder of the checkpointed generator)
 struct MemPriorW {

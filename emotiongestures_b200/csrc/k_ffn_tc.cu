@@ -18,6 +18,8 @@
 // same ring slot of all CL CTAs; a slot is refilled when the MMA warps of ALL CTAs have released it (tcgen05.commit
 // multicast onto every CTA's empty barrier); the X tiles and everything downstream stay private to a CTA.  Measured,
 // the weight stream is not what bounds the kernel (see g_ffn_cluster below), so CL = 1 is the default.
+#include <cstring>
+
 #include "egx_common.cuh"
 #include "tc_common.cuh"
 
@@ -38,13 +40,16 @@ constexpr int kStageBytes = 32 * 1024;
 constexpr int kFfnStages = 3;
 constexpr int kFfnSmem = kXBytes + 2 * kHBytes + kFfnStages * kStageBytes + 256 + 1024;
 
+constexpr int kFfnMaxInner = 2048;
+// By value in the kernel's constant bank (7 KB of parameters): the epilogues index the bias / LayerNorm vectors with
+// warp-uniform addresses every 32-column chunk, which the constant cache serves without an L2 round trip.
 struct FfnParams {
     int M, NJ;                     // rows, hidden chunks (d_inner / 128)
-    const float* b1;               // [d_inner]
-    const float* b2;               // [256]
     const float* resid;            // [M][256] fp32 residual (the FFN input)
-    const float* ln_g; const float* ln_b;
     float* out32; __half* out16;   // [M][256]
+    float b1[kFfnMaxInner];        // [d_inner]
+    float b2[FD], ln_g[FD], ln_b[FD];
+    unsigned long long* wait_cycles;   // attribution builds: [6] cycles the MMA thread of CTA 0 spent per wait kind + total
     int debug;                     // EGX_FFN_DEBUG (attribution builds only, wrong results): 1 = no weight loads, 2 = no
                                    // hidden-chunk conversion, 4 = no output epilogue work
 };
@@ -52,7 +57,7 @@ struct FfnParams {
 template <int CL>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-              const __grid_constant__ CUtensorMap tmW2, FfnParams p) {
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ FfnParams p) {
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     constexpr int kPiece = kStageBytes / CL;          // bytes of a stage one CTA fetches: a {64, 256 / CL} box
     constexpr int kPieceRows = 256 / CL;
@@ -157,15 +162,22 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             int st = 0;
             uint32_t ph = 0, it = 0;
             uint32_t n_g1[2] = {0, 0}, n_g2[2] = {0, 0};
+#ifdef EGX_ATTRIBUTION
+            unsigned long long wc[6] = {0, 0, 0, 0, 0, 0};
+            const long long t_begin = clock64();
+#define FFN_TIMED_WAIT(kind, bar, par) do { const long long _t = clock64(); mbar_wait(bar, par); wc[kind] += clock64() - _t; } while (0)
+#else
+#define FFN_TIMED_WAIT(kind, bar, par) mbar_wait(bar, par)
+#endif
             auto advance = [&]() { st = st + 1 == kFfnStages ? 0 : st + 1; ph ^= (st == 0); };
             auto gemm1 = [&](int j, bool last) {
                 const int b = j & 1;
-                mbar_wait(&hacc_empty[b], (n_g1[b] & 1) ^ 1);
+                FFN_TIMED_WAIT(1, &hacc_empty[b], (n_g1[b] & 1) ^ 1);
                 ++n_g1[b];
                 tc_fence_after();
                 const uint32_t d = tmem_H + b * FH;
                 for (int s2 = 0; s2 < 2; ++s2) {
-                    mbar_wait(&w_full[st], ph);
+                    FFN_TIMED_WAIT(2, &w_full[st], ph);
                     tc_fence_after();
                     const uint32_t w_lo = smem_desc_lo(smem_u32(ring + st * kStageBytes));
 #pragma unroll
@@ -184,11 +196,11 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             };
             auto gemm2 = [&](int j, bool last) {
                 const int b = j & 1;
-                mbar_wait(&hs_full[b], n_g2[b] & 1);
+                FFN_TIMED_WAIT(3, &hs_full[b], n_g2[b] & 1);
                 ++n_g2[b];
                 tc_fence_after();
                 for (int kb = 0; kb < 2; ++kb) {
-                    mbar_wait(&w_full[st], ph);
+                    FFN_TIMED_WAIT(2, &w_full[st], ph);
                     tc_fence_after();
                     const uint32_t w_lo = smem_desc_lo(smem_u32(ring + st * kStageBytes));
                     const uint32_t a_lo = h_lo + ((b * kHBytes + kb * 16384) >> 4);
@@ -202,16 +214,22 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 if (last) umma_commit(y_full);
             };
             for (; it < (uint32_t)n_iter; ++it) {
-                mbar_wait(x_full, it & 1);
+                FFN_TIMED_WAIT(0, x_full, it & 1);
                 tc_fence_after();
                 gemm1(0, NJ == 1);
                 gemm1(1, NJ == 2);
                 for (int j = 0; j < NJ; ++j) {
-                    if (j == 0) { mbar_wait(y_empty, (it & 1) ^ 1); tc_fence_after(); }
+                    if (j == 0) { FFN_TIMED_WAIT(4, y_empty, (it & 1) ^ 1); tc_fence_after(); }
                     gemm2(j, j == NJ - 1);
                     if (j + 2 < NJ) gemm1(j + 2, j + 3 == NJ);
                 }
             }
+#ifdef EGX_ATTRIBUTION
+            if (p.wait_cycles && blockIdx.x == 0) {
+                wc[5] = clock64() - t_begin;
+                for (int i = 0; i < 6; ++i) p.wait_cycles[i] = wc[i];
+            }
+#endif
         }
     } else if (warp < 10) {
         // hidden-chunk epilogue: TMEM -> + b1, ReLU, fp16 -> shared memory (SWIZZLE_128B K-major A operand of GEMM2)
@@ -225,7 +243,6 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 mbar_wait(&hacc_full[b], n & 1);
                 tc_fence_after();
                 mbar_wait(&hs_empty[b], (n & 1) ^ 1);
-                const float* b1 = p.b1 + j * FH;
                 if (p.debug & 2) {
                     tc_fence_before();
                     __syncwarp();
@@ -243,11 +260,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                         if (lane == 0) mbar_arrive(&hacc_empty[b]);
                     }
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(b1 + c * 32) + j4);
-                        v[4 * j4] = fmaxf(v[4 * j4] + bi.x, 0.f); v[4 * j4 + 1] = fmaxf(v[4 * j4 + 1] + bi.y, 0.f);
-                        v[4 * j4 + 2] = fmaxf(v[4 * j4 + 2] + bi.z, 0.f); v[4 * j4 + 3] = fmaxf(v[4 * j4 + 3] + bi.w, 0.f);
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e] + p.b1[j * FH + c * 32 + e], 0.f);
                     unsigned char* dst = hrow + (c >> 1) * 16384;           // 64-wide k-block of this 32-column chunk
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -266,23 +279,24 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
         }
     } else {
-        // output epilogue: Y + b2 + residual -> LayerNorm -> fp32 and fp16 rows
+        // output epilogue: Y + b2 + residual -> LayerNorm -> fp32 and fp16 rows.  Global accesses go through the
+        // 4-lane transposed layout (tc_common.cuh: seg_transpose4): one full 128-byte line per row and access instead
+        // of 32 bytes per line, which is what this epilogue is bound by; b2 and the LayerNorm parameters sit in the
+        // kernel's constant bank (no L2 round trip per 32-column chunk).
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t taddr = tmem_Y + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
         for (int tile = blockIdx.x; it < (uint32_t)n_iter; tile += gridDim.x, ++it) {
-            const int m = tile * FM + r;
-            const bool live = m < p.M;
-            const float* res = p.resid + (size_t)(live ? m : 0) * FD;
-            // this thread's residual row (1 KB) is pulled into L2 now: the epilogue below runs while the tensor pipe
-            // waits for the accumulator, so its loads must not pay DRAM latency
-            if (live) {
+            const int row0 = tile * FM + q * 32 + (lane & ~3);       // first row of this lane's group of four
+            uint32_t rn[32];
+            // this thread's residual row (1 KB = 8 lines) goes to L2 now, a whole tile of MMA time ahead of its use: the
+            // epilogue below runs while the tensor pipe waits for the accumulator and must not pay DRAM latency
+            if (tile * FM + r < p.M) {
+                const float* own = p.resid + (size_t)(tile * FM + r) * FD;
 #pragma unroll
-                for (int l = 1; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(res + l * 32));
+                for (int l = 0; l < 8; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(own + l * 32));
             }
-            float4 ad_n[8];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(res) + j4);
+            load_rows_t(p.resid, FD, row0, p.M, 0, lane, rn);
             mbar_wait(y_full, it & 1);
             tc_fence_after();
             if (p.debug & 4) {
@@ -297,16 +311,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 float v[32];
                 __syncwarp();
                 tmem_ld32(taddr + c * 32, v);
+                seg_transpose4<8>(rn, lane);                         // -> this thread's own row, columns in order
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 bi = (p.debug & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32) + j4);
-                    v[4 * j4] += bi.x + ad_n[j4].x; v[4 * j4 + 1] += bi.y + ad_n[j4].y;
-                    v[4 * j4 + 2] += bi.z + ad_n[j4].z; v[4 * j4 + 3] += bi.w + ad_n[j4].w;
-                }
-                if (c + 1 < FD / 32 && !(p.debug & 16)) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(res + (c + 1) * 32) + j4);
-                }
+                for (int j = 0; j < 32; ++j) v[j] += p.b2[c * 32 + j] + __uint_as_float(rn[j]);
+                if (c + 1 < FD / 32) load_rows_t(p.resid, FD, row0, p.M, (c + 1) * 32, lane, rn);
                 if (c == 0) v0 = v[0];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { const float d = v[j] - v0; s1 += d; s2 = fmaf(d, d, s2); }
@@ -327,36 +335,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                     if (lane == 0) mbar_arrive(y_empty);
                 }
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 g4 = (p.debug & 8) ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(reinterpret_cast<const float4*>(p.ln_g + c * 32) + j4);
-                    const float4 b4 = (p.debug & 8) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.ln_b + c * 32) + j4);
-                    v[4 * j4] = fmaf((v[4 * j4] - mean) * rstd, g4.x, b4.x);
-                    v[4 * j4 + 1] = fmaf((v[4 * j4 + 1] - mean) * rstd, g4.y, b4.y);
-                    v[4 * j4 + 2] = fmaf((v[4 * j4 + 2] - mean) * rstd, g4.z, b4.z);
-                    v[4 * j4 + 3] = fmaf((v[4 * j4 + 3] - mean) * rstd, g4.w, b4.w);
-                }
-                if (live && !(p.debug & 32)) {
-                    float* o32 = p.out32 + (size_t)m * FD + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o32 + 8 * j), "f"(v[8 * j]),
-                                     "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]),
-                                     "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
-                                     : "memory");
-                    __half* o16 = p.out16 + (size_t)m * FD + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint32_t u[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const __half2 h2 = __floats2half2_rn(v[16 * j + 2 * e], v[16 * j + 2 * e + 1]);
-                            u[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                        }
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o16 + 16 * j), "r"(u[0]),
-                                     "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
-                                     : "memory");
-                    }
-                }
+                for (int j = 0; j < 32; ++j) v[j] = fmaf((v[j] - mean) * rstd, p.ln_g[c * 32 + j], p.ln_b[c * 32 + j]);
+                store_rows_t(v, p.out32, FD, p.out16, FD, row0, p.M, c * 32, lane);
             }
         }
     }
@@ -401,14 +381,17 @@ int ffn_tc_init_device() {
 }
 
 // true when launch_ffn_tc can run this geometry (the callers fall back to the three-kernel chain otherwise)
-bool ffn_tc_supported(int d_model, int d_inner) { return d_model == FD && d_inner % (2 * FH) == 0 && d_inner >= 2 * FH; }
+bool ffn_tc_supported(int d_model, int d_inner) {
+    return d_model == FD && d_inner % (2 * FH) == 0 && d_inner >= 2 * FH && d_inner <= kFfnMaxInner;
+}
 
 // x16 [M][256] fp16 (the FFN input as the GEMM operand), resid [M][256] fp32 (the same input in fp32), w1 [d_inner][256],
-// w2 [256][d_inner] fp16 with pitches ldw1 / ldw2; out32 / out16 [M][256].  All pointers 32-byte aligned.
+// w2 [256][d_inner] fp16 with pitches ldw1 / ldw2; out32 / out16 [M][256], all 32-byte aligned device pointers.
+// b1 [d_inner], b2 / ln_g / ln_b [256] are HOST vectors: they travel as kernel parameters.
 int launch_ffn_tc(const __half* x16, const float* resid, const __half* w1, int ldw1, const float* b1, const __half* w2, int ldw2,
                   const float* b2, const float* ln_g, const float* ln_b, int M, int d_inner, float* out32, __half* out16,
                   cudaStream_t s) {
-    if (!ffn_tc_supported(FD, d_inner) || !b1 || !b2 || !resid || !out32 || !out16) return -1;
+    if (!ffn_tc_supported(FD, d_inner) || !b1 || !b2 || !ln_g || !ln_b || !resid || !out32 || !out16) return -1;
     CUtensorMap tx, t1, t2;
     const uint64_t dX[2] = {(uint64_t)FD, (uint64_t)M}, sXp[1] = {(uint64_t)FD * 2};
     const uint64_t d1[2] = {(uint64_t)FD, (uint64_t)d_inner}, s1[1] = {(uint64_t)ldw1 * 2};
@@ -419,7 +402,28 @@ int launch_ffn_tc(const __half* x16, const float* resid, const __half* w1, int l
     if (!make_tmap_f16(&tx, x16, 2, dX, sXp, bX, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     if (!make_tmap_f16(&t1, w1, 2, d1, s1, b1x, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     if (!make_tmap_f16(&t2, w2, 2, d2, s2, b2x, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    FfnParams p{M, d_inner / FH, b1, b2, resid, ln_g, ln_b, out32, out16, env_switch("EGX_FFN_DEBUG", 0)};
+    FfnParams p;
+    p.M = M; p.NJ = d_inner / FH; p.resid = resid; p.out32 = out32; p.out16 = out16;
+    std::memcpy(p.b1, b1, sizeof(float) * d_inner);
+    std::memcpy(p.b2, b2, sizeof(float) * FD);
+    std::memcpy(p.ln_g, ln_g, sizeof(float) * FD);
+    std::memcpy(p.ln_b, ln_b, sizeof(float) * FD);
+    p.debug = env_switch("EGX_FFN_DEBUG", 0);
+    p.wait_cycles = nullptr;
+#ifdef EGX_ATTRIBUTION
+    {   // MMA-thread wait attribution of the previous launch, printed when EGX_FFN_WAITS=1
+        static unsigned long long* dbg = nullptr;
+        if (env_switch("EGX_FFN_WAITS", 0)) {
+            if (!dbg) cudaMallocManaged(&dbg, 6 * sizeof(unsigned long long));
+            else {
+                cudaStreamSynchronize(s);
+                fprintf(stderr, "ffn waits (cycles): x_full %llu hacc_empty %llu w_full %llu hs_full %llu y_empty %llu total %llu\n", dbg[0],
+                        dbg[1], dbg[2], dbg[3], dbg[4], dbg[5]);
+            }
+            p.wait_cycles = dbg;
+        }
+    }
+#endif
     const int tiles = (M + FM - 1) / FM;
     if (cl == 4) return launch_ffn_cl<4>(tx, t1, t2, p, tiles, s);
     if (cl == 2) return launch_ffn_cl<2>(tx, t1, t2, p, tiles, s);

@@ -225,15 +225,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int m0, n0;
                 gemm_tile<BN, RES>(walk, (int)tcount, &m0, &n0);
                 const int m = m0 + row;
-                const bool live = m < M;
-                const float* add_row = (ep.addend && live) ? ep.addend + (size_t)m * ep.addend_ld : nullptr;
-                float4 ad_n[8];
-                if (add_row) {
-                    // the rest of the residual row goes to L2 now, its first chunk to registers
+                const int grow0 = m0 + q * 32 + (lane & ~3);      // first row of this lane's group of four
+                // global accesses go through the 4-lane transposed layout (tc_common.cuh: seg_transpose4): whole
+                // 128-byte lines per row and access; the row-per-thread pattern is bound by the L1 line rate
+                uint32_t rn[32];
+                if (ep.addend) {
+                    if (m < M) {
+                        const float* own = ep.addend + (size_t)m * ep.addend_ld;
 #pragma unroll
-                    for (int l = 1; l < BN / 32; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + l * 32));
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row) + j4);
+                        for (int l = 1; l < BN / 32; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(own + l * 32));
+                    }
+                    load_rows_t(ep.addend, ep.addend_ld, grow0, M, 0, lane, rn);
                 }
                 mbar_wait(&tmem_full[grp], (tcount >> 1) & 1);
                 tc_fence_after();
@@ -251,15 +253,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[4 * j4] += bi.x; v[4 * j4 + 1] += bi.y; v[4 * j4 + 2] += bi.z; v[4 * j4 + 3] += bi.w;
                         }
                     }
-                    if (add_row) {
+                    if (ep.addend) {
+                        seg_transpose4<8>(rn, lane);              // -> this thread's own row, columns in order
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            v[4 * j4] += ad_n[j4].x; v[4 * j4 + 1] += ad_n[j4].y; v[4 * j4 + 2] += ad_n[j4].z; v[4 * j4 + 3] += ad_n[j4].w;
-                        }
-                        if (c + 1 < BN / 32) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + (c + 1) * 32) + j4);
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rn[j]);
+                        if (c + 1 < BN / 32) load_rows_t(ep.addend, ep.addend_ld, grow0, M, (c + 1) * 32, lane, rn);
                     }
                     if (c == 0) v0 = v[0];
 #pragma unroll
@@ -284,9 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[4 * j4 + 2] = fmaf((v[4 * j4 + 2] - mean) * rstd, g4.z, b4.z);
                         v[4 * j4 + 3] = fmaf((v[4 * j4 + 3] - mean) * rstd, g4.w, b4.w);
                     }
-                    if (live)
-                        store_chunk32(v, ep.out32 ? ep.out32 + (size_t)m * ep.ld32 + c * 32 : nullptr,
-                                      ep.out16 ? ep.out16 + (size_t)m * ep.ld16 + c * 32 : nullptr);
+                    store_rows_t(v, ep.out32, BN, ep.out16, BN, grow0, M, c * 32, lane);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -333,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     gemm_named_bar(1 + grp, 128);
                 }
-                if (m < M || ep.tma16) {
+                {
                     const bool full_chunk = nb + 32 <= N;
                     if (full_chunk) {
                         // bias / ReLU / addend are uniform per launch: a Linear without them (the attention projections)
@@ -377,7 +373,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j4 = 0; j4 < 8; ++j4) ad_n[j4] = __ldg(reinterpret_cast<const float4*>(add_row + nb + 32) + j4);
                     }
                     if (ep.debug & 1) continue;
-                    if (ep.out32 && m < M) {
+                    // full chunks with vector-friendly pitches leave through the 4-lane transposed layout (whole lines
+                    // per access, tc_common.cuh); everything else one row per thread
+                    const bool t32 = ep.out32 && full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0;
+                    const bool t16 = ep.out16 && !ep.tma16 && full_chunk && (ep.ld16 & 7) == 0 &&
+                                     (reinterpret_cast<uintptr_t>(ep.out16) & 15) == 0;
+                    if (t32 || t16)
+                        store_rows_t(v, t32 ? ep.out32 : nullptr, ep.ld32, t16 ? ep.out16 : nullptr, ep.ld16,
+                                     m0 + q * 32 + (lane & ~3), M, nb, lane);
+                    if (ep.out32 && !t32 && m < M) {
                         float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
                         if (full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0) {
                             // 256-bit stores: every instruction writes whole 32-byte sectors
@@ -418,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((uint32_t)j ^ slab_swz) << 4)),
                                          "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
                         }
-                    } else if (ep.out16 && m < M) {
+                    } else if (ep.out16 && !t16 && m < M) {
                         __half* o = ep.out16 + (size_t)m * ep.ld16 + nb;
                         if (full_chunk && (ep.ld16 & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out16) & 31) == 0) {
 #pragma unroll
@@ -557,8 +561,8 @@ int launch_gemm_tc(const __half* A, int lda, const __half* W, int ldw, int M, in
         // LayerNorm epilogue: the tile must span the whole row (N == 256) and take the vector paths
         const auto al32 = [](const void* p_) { return (reinterpret_cast<uintptr_t>(p_) & 31) == 0; };
         if (N != 256 || !e.ln_b || e.relu || e.addend_rows != 0 || (e.addend && ((e.addend_ld & 3) || !al32(e.addend))) ||
-            (e.bias && !al32(e.bias)) || !al32(e.ln_g) || !al32(e.ln_b) || (out32 && ((ld32 & 7) || !al32(out32))) ||
-            (out16 && ((ld16 & 15) || !al32(out16))))
+            (e.bias && !al32(e.bias)) || !al32(e.ln_g) || !al32(e.ln_b) || (out32 && (ld32 != 256 || !al32(out32))) ||
+            (out16 && (ld16 != 256 || !al32(out16))))
             return -1;
         return launch_bn<256, false, true>(A, lda, W, ldw, M, N, K, ep, s);
     }

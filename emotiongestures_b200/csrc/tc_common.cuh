@@ -289,6 +289,83 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Coalescing for row-per-thread epilogues.  After tcgen05.ld.32x32b a thread owns 32 consecutive columns of ITS row, so
+// a warp-wide global access touches 32 different lines with 16-32 bytes each — the L1 processes one line per cycle
+// whatever the payload, and that line rate, not DRAM, bounds such an epilogue.  seg_transpose4 exchanges data inside
+// every group of 4 lanes: before, lane i holds segments 0..3 (SEG registers each) of its own row; after, it holds
+// segment i of the rows of lanes 0..3 of its group, so the four lanes of a group together cover ONE contiguous run per
+// access (128 bytes for 8-register fp32 segments).  Two butterfly steps (lane xor 1, lane xor 2); an involution.
+template <int SEG>
+__device__ __forceinline__ void seg_transpose4(uint32_t (&r)[4 * SEG], int lane) {
+    const bool odd = (lane & 1) != 0, hi = (lane & 2) != 0;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int e = 0; e < SEG; ++e) {
+            uint32_t& a = r[(2 * p) * SEG + e];
+            uint32_t& b = r[(2 * p + 1) * SEG + e];
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
+            if (odd) a = got; else b = got;
+        }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int e = 0; e < SEG; ++e) {
+            uint32_t& a = r[p * SEG + e];
+            uint32_t& b = r[(p + 2) * SEG + e];
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 2);
+            if (hi) a = got; else b = got;
+        }
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void stg128(void* p, const uint32_t* r) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// 32 columns of residual for the 4 rows of this lane's group, fetched in the transposed layout (lane i: columns
+// [8 i, 8 i + 8) of each row: one 128-byte line per row and group); rows >= n_rows give zeros
+__device__ __forceinline__ void load_rows_t(const float* base, int ld, int row0, int n_rows, int col0, int lane, uint32_t (&r)[32]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (row0 + k < n_rows) ldg256(base + (size_t)(row0 + k) * ld + col0 + 8 * (lane & 3), &r[8 * k]);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[8 * k + e] = 0u;
+        }
+    }
+}
+// v: 32 columns of this thread's own row -> fp32 and / or fp16 rows in global memory through the transposed layout
+__device__ __forceinline__ void store_rows_t(const float (&v)[32], float* o32, int ld32, __half* o16, int ld16, int row0, int n_rows,
+                                             int col0, int lane) {
+    if (o16) {
+        uint32_t h[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        seg_transpose4<4>(h, lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (row0 + k < n_rows) stg128(o16 + (size_t)(row0 + k) * ld16 + col0 + 8 * (lane & 3), &h[4 * k]);
+    }
+    if (o32) {
+        uint32_t w[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) w[e] = __float_as_uint(v[e]);
+        seg_transpose4<8>(w, lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (row0 + k < n_rows) stg256(o32 + (size_t)(row0 + k) * ld32 + col0 + 8 * (lane & 3), &w[8 * k]);
+    }
+}
+
 // 32 lanes x 16 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
