@@ -23,6 +23,7 @@
 #include "egx_common.cuh"
 #include "tc_common.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace egx {
@@ -41,6 +42,11 @@ struct ConvTcParams {
     int tiles_per_clip;
     int num_tiles;         // B * tiles_h * tiles_w
     uint32_t magic_tpc, magic_tw;   // ceil(2^40 / d) >> 8 style magics, see fast_div
+    int raster;            // halo kernels: tiles are runs of 128 positions of the clip's padded-width raster (see RASTER)
+    uint32_t magic_mw;     // fast_div magic of MW (raster)
+    int patch_bytes;       // halo kernels: bytes of one channel-chunk patch in shared memory (1024-aligned)
+    int n_stages;          // generic halo kernel: ring stages of kChunks patches
+    int b_stages;          // conv128 kernel: depth of the weight ring
     int ks, stride, pad;
     int cout;              // output channels of THIS launch (<= NPAD)
     int n_off, ldc;        // first output channel / channel pitch of the output map (cout > 128 runs as 128-wide slices)
@@ -67,6 +73,14 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic) { retur
 // (dy*(BW+2)+dx) rows.  TMA and UMMA both apply the 128B/64B swizzle on absolute shared-memory address
 // bits, so a row-shifted descriptor still sees the pattern TMA wrote.  L2->SM traffic per tile drops ~7x.
 constexpr int kPatchRows = 176;          // >= 128 + 2*(BW+2) + 2 with BW + 2 <= 20
+// RASTER (halo kernels whose map is narrow enough): instead of BH x BW patches — which leave 12-25% of the 128 MMA rows
+// unused because BH * (BW + 2) rarely comes near 128 and the last patch row of a map is mostly empty — a tile is a run
+// of 128 consecutive positions of the clip's raster with padded width MW = Wo + 2 (position g -> pixel (g / MW, g % MW),
+// columns Wo, Wo + 1 are the junk every halo tile already carries).  The shared-memory patch is R whole padded map rows
+// starting one row above the tile's first row (one 4-D TMA box {channels, MW, R, 1} at x = -1: out-of-bounds zero fill is
+// still the padding), and tap (dy, dx) is the patch read from row off + dy * MW + dx, off = the tile's first position
+// within its first row.  Tiles per TED clip: 80 -> 72 (layer 1), 22 -> 19 (layer 2), 6 -> 5 (layer 3).
+inline int raster_map_rows(int mw) { return (128 + 3 * mw) / mw + 1; }        // R: rows a tile's taps can reach
 
 // Output path of the epilogue
 enum { OUT_TMA = 0,      // NHWC fp16 through a swizzled shared-memory staging tile and one TMA box store per tile
@@ -84,7 +98,7 @@ struct ConvCfg {
     static constexpr bool kResidentB = kNumKb * kBBytes <= (HALO ? 112 : 80) * 1024;
     // K blocks handled per pipeline stage (one barrier round-trip): keep >= 4 MMAs of work per wait
     static constexpr int kKbPerStage = HALO ? kNumKb : ((CK == 32 && TAPS == 9) ? 3 : 1);
-    static constexpr int kPatchBytes = kPatchRows * kSwz;
+    static constexpr int kPatchBytes = kPatchRows * kSwz;     // HALO: the launch may size its patches differently (raster)
     static constexpr int kStageBytes = HALO ? kChunks * kPatchBytes
                                             : kKbPerStage * (kABytes + (kResidentB ? 0 : kBBytes));
     static constexpr int kResBytes = kResidentB ? kNumKb * kBBytes : 0;
@@ -94,10 +108,14 @@ struct ConvCfg {
     static constexpr int kOutBytes = OUT == OUT_TMA ? 4 * kOutTileBytes : 0;
     static constexpr int kTailBytes = 256 + 3 * 128 * 4 + 2 * 2 * 4 * 128 * 4 + 1024;   // barriers, params, SE sums, align
     static constexpr int kSmemBudget = 227 * 1024 - 512;
-    static constexpr int kStagesRaw = (kSmemBudget - kResBytes - kOutBytes - kTailBytes) / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    // the ring takes everything the other regions leave; HALO kernels partition it at run time (p.patch_bytes,
+    // p.n_stages: the patch size depends on the map width), the others into kStages stages of kStageBytes
+    static constexpr int kMaxStages = 8;
+    static constexpr int kRingBytes = (kSmemBudget - kResBytes - kOutBytes - kTailBytes) / 1024 * 1024;
+    static constexpr int kStagesRaw = kRingBytes / kStageBytes;
+    static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
     static constexpr int kStagesPerTile = kNumKb / kKbPerStage;
-    static constexpr int kOutOffset = kResBytes + kStages * kStageBytes;
+    static constexpr int kOutOffset = kResBytes + kRingBytes;
     static constexpr int kBarOffset = kOutOffset + kOutBytes;
     static constexpr int kParOffset = kBarOffset + 256;      // bias | scale | shift, 128 floats each
     static constexpr int kRedOffset = kParOffset + 3 * 128 * 4;   // [group][parity][4 warps][128] floats (SE sums)
@@ -199,8 +217,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned char* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
     unsigned char* ring = smem + S::kResBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
-    uint64_t* empty = full + S::kStages;
-    uint64_t* tmem_full = empty + S::kStages;      // [4]
+    uint64_t* empty = full + S::kMaxStages;
+    uint64_t* tmem_full = empty + S::kMaxStages;   // [4]
+    // ring geometry: compile-time for the streamed kernels, per launch for the halo kernels
+    const int n_stages = HALO ? p.n_stages : S::kStages;
+    const int patch_bytes = HALO ? p.patch_bytes : S::kPatchBytes;
+    const int stage_bytes = HALO ? S::kChunks * p.patch_bytes : S::kStageBytes;
     uint64_t* tmem_empty = tmem_full + 4;          // [4]
     uint64_t* b_full = tmem_empty + 4;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
@@ -215,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         if (OUT == OUT_TMA) prefetch_tmap(&tmO);
-        for (int i = 0; i < S::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         mbar_init(b_full, 1);
         fence_barrier_init();
@@ -247,17 +269,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tile = walk.t0 + n * walk.tstep;
                 const int b = tile / tiles_per_clip;
                 const int t = tile - b * tiles_per_clip;
-                const int wi0 = (t % p.tiles_w) * p.BW * p.stride - p.pad;
-                const int hi0 = (t / p.tiles_w) * p.BH * p.stride - p.pad;
+                int wi0 = (t % p.tiles_w) * p.BW * p.stride - p.pad;
+                int hi0 = (t / p.tiles_w) * p.BH * p.stride - p.pad;
+                if (HALO && p.raster) { wi0 = -1; hi0 = (t * 128) / p.MW - 1; }
                 if (HALO) {
-                    const int st = it % S::kStages;
-                    mbar_wait(&empty[st], ((it / S::kStages) & 1) ^ 1);
-                    unsigned char* dst = ring + st * S::kStageBytes;
+                    const int st = it % n_stages;
+                    mbar_wait(&empty[st], ((it / n_stages) & 1) ^ 1);
+                    unsigned char* dst = ring + st * stage_bytes;
                     if (p.debug & 2) { mbar_arrive(&full[st]); ++it; continue; }
                     mbar_expect_tx(&full[st], (uint32_t)S::kChunks * p.MW * (p.BH + 2) * S::kSwz);
 #pragma unroll
                     for (int ch = 0; ch < S::kChunks; ++ch)
-                        tma_load_4d(dst + ch * S::kPatchBytes, &tmA, &full[st], ch * S::CK, wi0, hi0, b);
+                        tma_load_4d(dst + ch * patch_bytes, &tmA, &full[st], ch * S::CK, wi0, hi0, b);
                     ++it;
                     continue;
                 }
@@ -304,10 +327,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * S::kAccStride;
                 if (HALO) {
-                    const int st = it % S::kStages;
-                    mbar_wait(&full[st], (it / S::kStages) & 1);
+                    const int st = it % n_stages;
+                    mbar_wait(&full[st], (it / n_stages) & 1);
                     tc_fence_after();
-                    const uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * S::kStageBytes));
+                    uint32_t a_lo = smem_desc_lo(smem_u32(ring + st * stage_bytes));
+                    if (p.raster) {                   // the tile starts `off` positions into its first map row
+                        const uint32_t tile = (uint32_t)(walk.t0 + (int)tcount * walk.tstep);
+                        const uint32_t g0 = (tile - fast_div(tile, p.magic_tpc) * tiles_per_clip) * 128u;
+                        a_lo += (g0 - fast_div(g0, p.magic_mw) * p.MW) * (S::kSwz >> 4);
+                    }
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const uint32_t a_tap = a_lo + row_off[tap / 3] + (tap % 3) * (S::kSwz >> 4);
@@ -315,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int ch = 0; ch < S::kChunks; ++ch) {
 #pragma unroll
                             for (int k = 0; k < S::CK / 16; ++k)
-                                umma_f16_lo<kDescHi>(d, a_tap + ((ch * S::kPatchBytes + k * 32) >> 4),
+                                umma_f16_lo<kDescHi>(d, a_tap + ((ch * patch_bytes + k * 32) >> 4),
                                                      b_lo + (((tap * S::kChunks + ch) * S::kBBytes + k * 32) >> 4), idesc,
                                                      (tap | ch | k) != 0);
                         }
@@ -351,7 +379,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = q * 32 + lane;              // accumulator row = M index of this thread's pixel
         const int ph_ = r / p.MW, pw_ = r % p.MW;
         const bool in_patch = ph_ < p.BH && pw_ < p.BW;
-        const int orow = ph_ * p.BW + pw_;        // row of the dense BH x BW output box
+        // row of the staged output tile: the dense BH x BW box, or (raster) the tile position itself
+        const int orow = p.raster ? r : ph_ * p.BW + pw_;
         const bool relu_first = p.relu_first != 0;
         const bool has_bias = p.bias != nullptr;
         constexpr bool se = MODE == MODE_SE, gated = MODE == MODE_GATED;
@@ -368,7 +397,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < kCopyIters; ++i) {
             const int id = i * 128 + r, row = id / kChunksPerRow, ck = id % kChunksPerRow;
-            cp_ph[i] = row < p.BH * p.BW ? row / p.BW : -1;
+            cp_ph[i] = p.raster ? row : (row < p.BH * p.BW ? row / p.BW : -1);     // raster: the tile position
             cp_pw[i] = row % p.BW;
             cp_src[i] = row * S::kOutRowBytes + ((ck ^ (S::kOutRowBytes == 64 ? ((row >> 1) & 3) : (row & 7))) << 4);
             cp_dst[i] = (uint32_t)((cp_ph[i] * p.Wo + cp_pw[i]) * S::kOutRowBytes + ck * 16);
@@ -391,8 +420,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t = (uint32_t)tile - b * tiles_per_clip;
             const uint32_t th = fast_div(t, p.magic_tw);
             const uint32_t tw = t - th * p.tiles_w;
-            const int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
-            const bool valid = in_patch && ho < p.Ho && wo < p.Wo;
+            int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
+            bool valid = in_patch && ho < p.Ho && wo < p.Wo;
+            if (p.raster) {
+                const uint32_t g = t * 128u + r;
+                ho = (int)fast_div(g, p.magic_mw); wo = (int)(g - (uint32_t)ho * p.MW);
+                valid = ho < p.Ho && wo < p.Wo;
+            }
             const uint32_t par_buf = n_local & 1;
             const uint32_t acc = tcount & 3;
             // gated: everything that does not depend on the accumulator is requested before waiting for it
@@ -425,10 +459,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 const uint32_t nt = (uint32_t)tile + 2 * walk.tstep;      // this group's next tile: residual -> L2
-                if ((int)tcount + 2 < walk.count && in_patch && !(p.debug & 64)) {
+                if ((int)tcount + 2 < walk.count && (in_patch || p.raster) && !(p.debug & 64)) {
                     const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * tiles_per_clip;
                     const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
-                    const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    if (p.raster) {
+                        const uint32_t g2 = t2 * 128u + r;
+                        ho2 = (int)fast_div(g2, p.magic_mw); wo2 = (int)(g2 - (uint32_t)ho2 * p.MW);
+                    }
                     if (ho2 < p.Ho && wo2 < p.Wo) {
                         const __half* np = p.res + (((size_t)b2 * p.Ho + ho2) * p.Wo + wo2) * p.ldc + p.n_off;
                         prefetch_l2(np);
@@ -488,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 }
                 if (OUT == OUT_TMA) {
-                    if (in_patch) {
+                    if (in_patch || p.raster) {
                         const uint32_t row = stage_u32 + par_buf * S::kOutTileBytes;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -500,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (valid) {
                         const size_t pix = ((size_t)b * p.Ho + ho) * p.Wo + wo;
                         __half* o = p.out + pix * p.ldc + p.n_off + nb;     // cout is a multiple of 32 on this path
-                        // 256-bit stores: every thread writes whole 32-byte sectors
+                        // 256-bit stores: every thread writes whole 32-byte sectors (consecutive lanes = consecutive pixels)
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
                             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 16 * j),
@@ -550,6 +588,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t src0 = smem_u32(smem + S::kOutOffset) + (grp * 2 + par_buf) * S::kOutTileBytes;
                     const int h0 = (int)th * p.BH, w0 = (int)tw * p.BW;
                     __half* tile_out = p.out + (((size_t)b * p.Ho + h0) * p.Wo + w0) * NPAD;
+                    if (p.raster) {
+                        // a tile's pixels are one contiguous run of the output map minus the two junk columns per row
+                        __half* clip_out = p.out + (size_t)b * p.Ho * p.Wo * NPAD;
+#pragma unroll
+                        for (int i = 0; i < kCopyIters; ++i) {
+                            const uint32_t g = t * 128u + (uint32_t)cp_ph[i];
+                            const uint32_t gy = fast_div(g, p.magic_mw), gx = g - gy * p.MW;
+                            if (gy < (uint32_t)p.Ho && gx < (uint32_t)p.Wo) {
+                                uint4 u;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(src0 + cp_src[i]));
+                                const int ck = (i * 128 + r) % kChunksPerRow;
+                                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(clip_out) +
+                                                          (size_t)(gy * p.Wo + gx) * S::kOutRowBytes + ck * 16) = u;
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int i = 0; i < kCopyIters; ++i) {
                         if (cp_ph[i] >= 0 && h0 + cp_ph[i] < p.Ho && w0 + cp_pw[i] < p.Wo) {
@@ -588,17 +643,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // warp 0: TMA producer; warps 1,2: one MMA issuer per tile of the pair; warp 3: TMEM alloc; warps 4-11: two epilogue
 // groups (one per tile of the pair), accumulators double-buffered across super-tiles (2 x 2 x 128 TMEM columns).
 // =================================================================================================================
+// Shared-memory layout (runtime: the patch size depends on the map width): [4 patches: tile 2 x half 2][weight ring:
+// b_stages x 16 KB][barriers 256 B][bias|scale|shift 1.5 KB][SE sums / gates 8 KB]; everything 1024-byte aligned.
 struct C128 {
-    static constexpr int kPatchBytes = kPatchRows * 128;          // one 64-channel half of one tile's patch
     static constexpr int kBBytes = 128 * 128;                     // 128 couts x 64 channels of one tap
-    static constexpr int kBStages = 7;
-    static constexpr int kAOffset = 0;                            // [tile 2][half 2]
-    static constexpr int kBOffset = 4 * kPatchBytes;
-    static constexpr int kBarOffset = kBOffset + kBStages * kBBytes;
-    static constexpr int kParOffset = kBarOffset + 256;
-    static constexpr int kRedOffset = kParOffset + 3 * 128 * 4;
-    static constexpr int kTotal = kRedOffset + 2 * 2 * 4 * 128 * 4 + 1024;
-    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+    static constexpr int kMaxBStages = 7;
+    static constexpr int kTailBytes = 256 + 3 * 128 * 4 + 2 * 2 * 4 * 128 * 4 + 1024;
+    static constexpr int kBudget = 227 * 1024;
+    static constexpr int kTotal = kBudget;                        // opt-in maximum; a launch asks for what it lays out
+    static int b_stages(int patch_bytes) {
+        const int n = (kBudget - kTailBytes - 4 * patch_bytes) / kBBytes;
+        return n > kMaxBStages ? kMaxBStages : n;
+    }
+    static int total(int patch_bytes, int stages) { return 4 * patch_bytes + stages * kBBytes + kTailBytes; }
 };
 
 template <int MODE>
@@ -607,14 +664,18 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     using S = C128;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);    // [tile * 2 + half]
+    const int kPatchBytes = p.patch_bytes, kBStages = p.b_stages;
+    const int kBOffset = 4 * kPatchBytes, kBarOffset = kBOffset + kBStages * S::kBBytes;
+    const int kParOffset = kBarOffset + 256, kRedOffset = kParOffset + 3 * 128 * 4;
+    constexpr int kAOffset = 0;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kBarOffset);    // [tile * 2 + half]
     uint64_t* a_empty = a_full + 4;
     uint64_t* b_full = a_empty + 4;
-    uint64_t* b_empty = b_full + S::kBStages;
-    uint64_t* tmem_full = b_empty + S::kBStages;     // [buf * 2 + tile]
+    uint64_t* b_empty = b_full + S::kMaxBStages;
+    uint64_t* tmem_full = b_empty + S::kMaxBStages;     // [buf * 2 + tile]
     uint64_t* tmem_empty = tmem_full + 4;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 4);
-    float* par = reinterpret_cast<float*>(smem + S::kParOffset);
+    float* par = reinterpret_cast<float*>(smem + kParOffset);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileWalk walk = tile_walk((p.num_tiles + 1) >> 1, p.contig);     // over super-tiles (pairs of tiles)
@@ -623,7 +684,7 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < S::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
         for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_barrier_init();
     }
@@ -653,6 +714,7 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t b = fast_div(tile, p.magic_tpc), tt = tile - b * p.tiles_per_clip;
                     const uint32_t th = fast_div(tt, p.magic_tw), tw = tt - th * p.tiles_w;
                     wi0[t] = (int)tw * p.BW - 1; hi0[t] = (int)th * p.BH - 1; bb[t] = (int)b;   // clip >= B: zero fill
+                    if (p.raster) { wi0[t] = -1; hi0[t] = (int)fast_div(tt * 128u, p.magic_mw) - 1; }
                 }
 #pragma unroll 1
                 for (int ch = 0; ch < 2; ++ch) {
@@ -660,15 +722,15 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int t = 0; t < 2; ++t) {
                         mbar_wait(&a_empty[t * 2 + ch], (n & 1) ^ 1);
                         mbar_expect_tx(&a_full[t * 2 + ch], a_tx);
-                        tma_load_4d(smem + S::kAOffset + (t * 2 + ch) * S::kPatchBytes, &tmA, &a_full[t * 2 + ch], ch * 64,
+                        tma_load_4d(smem + kAOffset + (t * 2 + ch) * kPatchBytes, &tmA, &a_full[t * 2 + ch], ch * 64,
                                     wi0[t], hi0[t], bb[t]);
                     }
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++it) {
-                        const int st = it % S::kBStages;
-                        mbar_wait(&b_empty[st], ((it / S::kBStages) & 1) ^ 1);
+                        const int st = it % kBStages;
+                        mbar_wait(&b_empty[st], ((it / kBStages) & 1) ^ 1);
                         mbar_expect_tx(&b_full[st], S::kBBytes);
-                        tma_load_2d(smem + S::kBOffset + st * S::kBBytes, &tmB, &b_full[st], tap * 128 + ch * 64, 0);
+                        tma_load_2d(smem + kBOffset + st * S::kBBytes, &tmB, &b_full[st], tap * 128 + ch * 64, 0);
                     }
                 }
             }
@@ -679,8 +741,8 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(128, 128);
             constexpr uint32_t kDescHi = smem_desc_hi<128>();
-            const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem + S::kBOffset));
-            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + S::kAOffset + t * 2 * S::kPatchBytes));
+            const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem + kBOffset));
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + kAOffset + t * 2 * kPatchBytes));
             const uint32_t row_off[3] = {0u, (uint32_t)(p.MW * 128) >> 4, (uint32_t)(2 * p.MW * 128) >> 4};
             uint32_t it = 0;
             for (uint32_t n = 0; (int)n < walk.count; ++n) {
@@ -688,15 +750,21 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&tmem_empty[buf * 2 + t], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (buf * 2 + t) * 128;
+                uint32_t off_units = 0;               // raster: the tile starts `off` positions into its first map row
+                if (p.raster) {
+                    const uint32_t tile = 2u * (uint32_t)(walk.t0 + (int)n * walk.tstep) + t;
+                    const uint32_t g0 = (tile - fast_div(tile, p.magic_tpc) * p.tiles_per_clip) * 128u;
+                    off_units = (g0 - fast_div(g0, p.magic_mw) * p.MW) * (128u >> 4);
+                }
 #pragma unroll 1
                 for (int ch = 0; ch < 2; ++ch) {
                     mbar_wait(&a_full[t * 2 + ch], n & 1);
                     tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + ((ch * S::kPatchBytes) >> 4);
+                    const uint32_t a_lo = a_lo0 + ((ch * kPatchBytes) >> 4) + off_units;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap, ++it) {
-                        const int st = it % S::kBStages;
-                        mbar_wait(&b_full[st], (it / S::kBStages) & 1);
+                        const int st = it % kBStages;
+                        mbar_wait(&b_full[st], (it / kBStages) & 1);
                         tc_fence_after();
                         const uint32_t a_tap = a_lo + row_off[tap / 3] + (tap % 3) * (128 >> 4);
                         const uint32_t b_lo = b_lo0 + ((st * S::kBBytes) >> 4);
@@ -723,7 +791,7 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool has_bias = p.bias != nullptr;
         constexpr bool se = MODE == MODE_SE, gated = MODE == MODE_GATED;
         const uint32_t par_u32 = smem_u32(par);
-        const uint32_t red_u32 = smem_u32(smem + S::kRedOffset) + grp * (2 * 512 * 4);
+        const uint32_t red_u32 = smem_u32(smem + kRedOffset) + grp * (2 * 512 * 4);
         Res32 rr = {};
         uint32_t cur_b = 0xffffffffu, gsel = 0;      // clip whose folded gate sits in shared-memory buffer gsel
         uint32_t gate_u32 = red_u32;
@@ -732,9 +800,14 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t tile = 2 * u + grp;
             const uint32_t b = fast_div(tile, p.magic_tpc), tt = tile - b * p.tiles_per_clip;
             const uint32_t th = fast_div(tt, p.magic_tw), tw = tt - th * p.tiles_w;
-            const int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
+            int ho = th * p.BH + ph_, wo = tw * p.BW + pw_;
             const bool live = tile < (uint32_t)p.num_tiles;
-            const bool valid = live && in_patch && ho < p.Ho && wo < p.Wo;
+            bool valid = live && in_patch && ho < p.Ho && wo < p.Wo;
+            if (p.raster) {
+                const uint32_t g = tt * 128u + r;
+                ho = (int)fast_div(g, p.magic_mw); wo = (int)(g - (uint32_t)ho * p.MW);
+                valid = live && ho < p.Ho && wo < p.Wo;
+            }
             const uint32_t buf = n & 1, par_buf = n & 1;
             const __half* res_pix = nullptr;
             if (gated) {
@@ -753,10 +826,14 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     named_bar_sync(1 + grp, 128);
                 }
                 const uint32_t nt = 2 * (u + walk.tstep) + grp;           // this group's next tile: residual -> L2
-                if ((int)n + 1 < walk.count && nt < (uint32_t)p.num_tiles && in_patch && !(p.debug & 64)) {
+                if ((int)n + 1 < walk.count && nt < (uint32_t)p.num_tiles && (in_patch || p.raster) && !(p.debug & 64)) {
                     const uint32_t b2 = fast_div(nt, p.magic_tpc), t2 = nt - b2 * p.tiles_per_clip;
                     const uint32_t th2 = fast_div(t2, p.magic_tw), tw2 = t2 - th2 * p.tiles_w;
-                    const int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    int ho2 = th2 * p.BH + ph_, wo2 = tw2 * p.BW + pw_;
+                    if (p.raster) {
+                        const uint32_t g2 = t2 * 128u + r;
+                        ho2 = (int)fast_div(g2, p.magic_mw); wo2 = (int)(g2 - (uint32_t)ho2 * p.MW);
+                    }
                     if (ho2 < p.Ho && wo2 < p.Wo) {
                         const __half* np = p.res + (((size_t)b2 * p.Ho + ho2) * p.Wo + wo2) * 128;
                         prefetch_l2(np);
@@ -829,7 +906,7 @@ conv128_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (se) {
                 named_bar_sync(1 + grp, 128);
                 if (live) {
-                    const float* red = reinterpret_cast<const float*>(smem + S::kRedOffset) + grp * 1024 + par_buf * 512;
+                    const float* red = reinterpret_cast<const float*>(smem + kRedOffset) + grp * 1024 + par_buf * 512;
                     p.se_part[(size_t)tile * 128 + r] = (red[r] + red[128 + r]) + (red[256 + r] + red[384 + r]);
                 }
             }
@@ -864,8 +941,38 @@ void pick_halo_patch(int Ho, int Wo, int* bw, int* bh) {
     }
 }
 
+// Raster tiling applies when the padded rows a tile can touch fit the kernel's patch buffer
+// bytes of shared memory a raster tile's patches may take in the kernel that runs (cin -> cin, 3x3): half of the generic
+// halo kernel's ring (>= 2 stages), or what leaves conv128 a 3-deep weight ring
+int raster_stage_cap(int cin) {
+    if (cin == 32) return ConvCfg<32, 32, 9, true, OUT_TMA>::kRingBytes / 2;     // the smaller ring of the two output paths
+    if (cin == 64) return ConvCfg<64, 64, 9, true, OUT_TMA>::kRingBytes / 2;
+    return 0;
+}
+bool raster_geometry(int cin, int Ho, int Wo, int* mw, int* rows) {
+    *mw = Wo + 2;
+    *rows = raster_map_rows(*mw);
+    if (*mw > 256 || *rows > 256 || Ho < 1) return false;
+    const int ck = cin < 64 ? cin : 64, chunks = cin / ck;
+    const int patch = (*rows * *mw * ck * 2 + 1023) / 1024 * 1024;
+    if (cin >= 128) return (C128::kBudget - C128::kTailBytes - 4 * patch) / C128::kBBytes >= 3;
+    return chunks * patch <= raster_stage_cap(cin);
+}
+void set_raster(ConvTcParams& p, int B, int mw, int rows) {
+    p.raster = 1;
+    p.BW = p.Wo; p.MW = mw; p.BH = rows - 2;         // the TMA box is {channels, MW, BH + 2, 1}
+    p.tiles_w = 1;
+    p.tiles_per_clip = (p.Ho * mw + 127) / 128;
+    p.tiles_h = p.tiles_per_clip;
+    p.num_tiles = B * p.tiles_per_clip;
+    p.magic_mw = make_magic((uint32_t)mw);
+}
+
+bool use_raster_fwd(int cin, int Ho, int Wo);
+
 int g_num_sms = 0;
 int g_debug = 0;
+int g_raster = 1;       // EGX_CONV_RASTER (attribution builds) bits: 1 = raster tiles for the 64 / 128-channel halo kernels, 2 = 32-channel
 int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
 int g_contig = 0;    // EGX_CONV_CONTIG: 1 = contiguous tile runs per CTA, 0 = strided walk (default: measured faster, the CTAs share halos in L2)
 int g_halo = 7;       // EGX_CONV_HALO bits: 1 = 64->64 convs, 2 = 32->32, 4 = 128->128, 8 = final conv (128 -> <= 48, NCHW out)
@@ -885,6 +992,17 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
     p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
     p.tiles_per_clip = p.tiles_w * p.tiles_h;
     p.num_tiles = B * p.tiles_per_clip;
+    p.raster = 0; p.magic_mw = 0; p.b_stages = 0;
+    {
+        int mw, rows;
+        if (HALO && OUT != OUT_NCHW && CIN == NPAD && CIN <= 64 && use_raster_fwd(CIN, p.Ho, p.Wo) && raster_geometry(CIN, p.Ho, p.Wo, &mw, &rows))
+            set_raster(p, B, mw, rows);
+    }
+    // rows a tap-shifted 128-row operand can reach: the whole box, and (patch tiles) 128 + 2 MW + 2 rows from its start
+    p.patch_bytes = HALO ? (std::max(p.MW * (p.BH + 2), p.raster ? 0 : 128 + 2 * p.MW + 2) * S::kSwz + 1023) / 1024 * 1024
+                         : S::kPatchBytes;
+    p.n_stages = HALO ? std::min<int>(S::kMaxStages, S::kRingBytes / (S::kChunks * p.patch_bytes)) : S::kStages;
+    if (p.n_stages < 2) return -1;
     if ((uint64_t)p.num_tiles * (uint64_t)p.tiles_per_clip >= (1ull << 32)) return -1;   // fast_div exactness
     p.magic_tpc = make_magic((uint32_t)p.tiles_per_clip);
     p.magic_tw = make_magic((uint32_t)p.tiles_w);
@@ -934,6 +1052,14 @@ int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     p.tiles_h = (p.Ho + p.BH - 1) / p.BH;
     p.tiles_per_clip = p.tiles_w * p.tiles_h;
     p.num_tiles = B * p.tiles_per_clip;
+    p.raster = 0; p.magic_mw = 0;
+    {
+        int mw, rows;
+        if (use_raster_fwd(128, p.Ho, p.Wo) && raster_geometry(128, p.Ho, p.Wo, &mw, &rows)) set_raster(p, B, mw, rows);
+    }
+    p.patch_bytes = ((p.raster ? (p.BH + 2) * p.MW : kPatchRows) * 128 + 1023) / 1024 * 1024;
+    p.b_stages = C128::b_stages(p.patch_bytes);
+    if (p.b_stages < 3) return -1;
     if ((uint64_t)(p.num_tiles + 1) * (uint64_t)p.tiles_per_clip >= (1ull << 32)) return -1;
     p.magic_tpc = make_magic((uint32_t)p.tiles_per_clip);
     p.magic_tw = make_magic((uint32_t)p.tiles_w);
@@ -952,9 +1078,10 @@ int launch_conv128(const ConvW& c, const __half* in, int B, int Hin, int Win, __
     if (!make_tmap_f16(&tb, c.w16, 2, dB, sB, bB, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     const int n_super = (p.num_tiles + 1) / 2;
     const int grid = n_super < g_num_sms ? n_super : g_num_sms;
-    if (gate) conv128_tc_kernel<MODE_GATED><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
-    else if (se_part) conv128_tc_kernel<MODE_SE><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
-    else conv128_tc_kernel<MODE_PLAIN><<<grid, kConvThreads, C128::kTotal, s>>>(ta, tb, p);
+    const int smem_bytes = C128::total(p.patch_bytes, p.b_stages);
+    if (gate) conv128_tc_kernel<MODE_GATED><<<grid, kConvThreads, smem_bytes, s>>>(ta, tb, p);
+    else if (se_part) conv128_tc_kernel<MODE_SE><<<grid, kConvThreads, smem_bytes, s>>>(ta, tb, p);
+    else conv128_tc_kernel<MODE_PLAIN><<<grid, kConvThreads, smem_bytes, s>>>(ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -995,6 +1122,7 @@ int conv_tc_init_device() {
     g_debug = env_switch("EGX_CONV_DEBUG", 0);
     g_out_direct = env_switch("EGX_CONV_OUT", g_out_direct);
     g_contig = env_switch("EGX_CONV_CONTIG", g_contig);
+    g_raster = env_switch("EGX_CONV_RASTER", g_raster);
     int rc = 0;
     rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
     rc |= cudaFuncSetAttribute(conv128_tc_kernel<MODE_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kTotal) == cudaSuccess ? 0 : -1;
@@ -1019,10 +1147,21 @@ static bool use_halo(int cin, int cout, int ks, int stride, int nchw) {
 }
 
 // SE partial-sum slots a conv writes per clip (tiles per clip) for an Ho x Wo output map
+// Layer 1 keeps patch tiles: at MW = 72 a raster tile spans 1.8 map rows but loads five (2.8x its outputs against 1.4x for
+// a 14 x 8 patch), and that stage is already close to its memory roofline (measured: 8.4 -> 8.9 ms/step with raster tiles)
+static bool use_raster(int cin, int Ho, int Wo) {
+    int mw, rows;
+    return (g_raster & (cin >= 64 ? 1 : 2)) && raster_geometry(cin, Ho, Wo, &mw, &rows);
+}
+
+namespace { bool use_raster_fwd(int cin, int Ho, int Wo) { return use_raster(cin, Ho, Wo); } }
+
 int conv_tc_tiles_per_clip(int cin, int cout, int Ho, int Wo) {
     int bw, bh;
-    if (use_halo(cin, cout, 3, 1, 0)) pick_halo_patch(Ho, Wo, &bw, &bh);
-    else pick_patch(Ho, Wo, &bw, &bh);
+    if (use_halo(cin, cout, 3, 1, 0)) {
+        if (use_raster(cin, Ho, Wo)) return (Ho * (Wo + 2) + 127) / 128;
+        pick_halo_patch(Ho, Wo, &bw, &bh);
+    } else pick_patch(Ho, Wo, &bw, &bh);
     return ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
 }
 
