@@ -174,7 +174,7 @@ attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int 
 // output column): its weights sit in shared memory as [c][k][f] so that a thread producing 4 frames x 1 column
 // issues 3 broadcast 16-byte weight loads + 3 activation loads per 12 FMAs.
 template <class T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
                   const float* __restrict__ w1, const float* __restrict__ b1,
                   const float* __restrict__ s1, const float* __restrict__ t1,
@@ -205,24 +205,39 @@ prior_conv_kernel(const float* __restrict__ prior, int p, int F, int P,
         mid[f * PW + x + 1] = fmaxf(a, 0.f) * s1[f] + t1[f];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (F4 / 4) * P; i += blockDim.x) {
-        const int fg = i / P, x = i % P;
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+    // a thread produces 4 frames x 4 columns: per input frame 3 broadcast weight loads and 6 activations for 48 FMAs
+    // (the 4 x 1 version was bound by its shared-memory loads: 6 per 12 FMAs)
+    const int XG = (P + 3) / 4;
+    for (int i = threadIdx.x; i < (F4 / 4) * XG; i += blockDim.x) {
+        const int fg = i / XG, x0 = (i % XG) * 4;
+        float a[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a[j][e] = 0.f;
         for (int c = 0; c < F; ++c) {
-            const float* m = mid + c * PW + x;
-            const float m0 = m[0], m1 = m[1], m2 = m[2];
+            const float* m = mid + c * PW + x0;
+            float mv[6];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) mv[e] = x0 + e < PW ? m[e] : 0.f;
             const float4 wa = *reinterpret_cast<const float4*>(w2s + (c * 3 + 0) * F4 + fg * 4);
             const float4 wb = *reinterpret_cast<const float4*>(w2s + (c * 3 + 1) * F4 + fg * 4);
             const float4 wc = *reinterpret_cast<const float4*>(w2s + (c * 3 + 2) * F4 + fg * 4);
-            a[0] = fmaf(wa.x, m0, fmaf(wb.x, m1, fmaf(wc.x, m2, a[0])));
-            a[1] = fmaf(wa.y, m0, fmaf(wb.y, m1, fmaf(wc.y, m2, a[1])));
-            a[2] = fmaf(wa.z, m0, fmaf(wb.z, m1, fmaf(wc.z, m2, a[2])));
-            a[3] = fmaf(wa.w, m0, fmaf(wb.w, m1, fmaf(wc.w, m2, a[3])));
+            const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2v[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    a[j][e] = fmaf(w0[j], mv[e], fmaf(w1[j], mv[e + 1], fmaf(w2v[j], mv[e + 2], a[j][e])));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int f = fg * 4 + j;
-            if (f < F) out[((size_t)b * F + f) * ldo + x] = T(fmaxf(a[j] + b2[f], 0.f) * s2[f] + t2[f]);
+            if (f >= F) continue;
+            const float bb = b2[f], ss = s2[f], tt = t2[f];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (x0 + e < P) out[((size_t)b * F + f) * ldo + x0 + e] = T(fmaxf(a[j][e] + bb, 0.f) * ss + tt);
         }
     }
 }
@@ -299,7 +314,10 @@ int launch_prior_conv(const Weights& w, const float* prior, int B, int p, int F,
     const size_t smem = sizeof(float) * ((size_t)(p + F) * (P + 2) + (size_t)F * 3 * ((F + 3) & ~3));
     if (cudaFuncSetAttribute(prior_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -1;
-    prior_conv_kernel<T><<<B, 256, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,
+    // one (4-frame, 4-column) item per thread where the geometry allows (TED: 9 x 32 = 288)
+    const int items = (((F + 3) & ~3) / 4) * ((P + 3) / 4);
+    const int threads = std::min(1024, std::max(128, (items + 31) / 32 * 32));
+    prior_conv_kernel<T><<<B, threads, smem, s>>>(prior, p, F, P, w.p_c1w, w.p_c1b, w.p_s1, w.p_t1,
                                               w.p_c2wt, w.p_c2b, w.p_s2, w.p_t2, out, ldo);
     return ok() ? 1 : -1;
 }
