@@ -343,11 +343,8 @@ int num_sms() {
 
 int launch_cvae_mlp(const CvaeW& w, const float* x, const float* y, const float* noise, int noise_is_z, int64_t n,
                     float* out, float* mu, float* logvar, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(cvae_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvaeSmem)) != cudaSuccess) return -1;
-        attr = true;
-    }
+    // the opt-in shared-memory size is a per-device function attribute: set it on every launch (cheap, no global state)
+    if (cudaFuncSetAttribute(cvae_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvaeSmem)) != cudaSuccess) return -1;
     const int grid = (int)std::min<int64_t>((n + CV_TILE - 1) / CV_TILE, (int64_t)num_sms() * 2);
     cvae_mlp_kernel<<<grid, CV_TILE, sizeof(CvaeSmem), s>>>(w, x, y, noise, noise_is_z, n, out, mu, logvar);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -355,11 +352,7 @@ int launch_cvae_mlp(const CvaeW& w, const float* x, const float* y, const float*
 
 int launch_cvae3_sample(const Cvae3W& w, const float* y, const float* z, int n, float* out, cudaStream_t s) {
     const int smem = (60 * 512 + 32 * 512) * 4;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(cvae3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        attr = true;
-    }
+    if (cudaFuncSetAttribute(cvae3_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
     const int grid = std::min(n, num_sms());
     cvae3_sample_kernel<<<grid, E1_THREADS, smem, s>>>(w, y, z, n, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

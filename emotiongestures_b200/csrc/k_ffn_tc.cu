@@ -336,7 +336,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaf((v[j] - mean) * rstd, p.ln_g[c * 32 + j], p.ln_b[c * 32 + j]);
-                store_rows_t(v, p.out32, FD, p.out16, FD, row0, p.M, c * 32, lane);
+                store_rows_t(v, p.out32, FD, p.out16, FD, row0, p.M, c * 32, lane, (p.debug & 128) != 0);
             }
         }
     }

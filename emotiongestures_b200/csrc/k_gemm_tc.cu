@@ -282,7 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[4 * j4 + 2] = fmaf((v[4 * j4 + 2] - mean) * rstd, g4.z, b4.z);
                         v[4 * j4 + 3] = fmaf((v[4 * j4 + 3] - mean) * rstd, g4.w, b4.w);
                     }
-                    store_rows_t(v, ep.out32, BN, ep.out16, BN, grow0, M, c * 32, lane);
+                    store_rows_t(v, ep.out32, BN, ep.out16, BN, grow0, M, c * 32, lane, (ep.debug & 128) != 0);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -380,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      (reinterpret_cast<uintptr_t>(ep.out16) & 15) == 0;
                     if (t32 || t16)
                         store_rows_t(v, t32 ? ep.out32 : nullptr, ep.ld32, t16 ? ep.out16 : nullptr, ep.ld16,
-                                     m0 + q * 32 + (lane & ~3), M, nb, lane);
+                                     m0 + q * 32 + (lane & ~3), M, nb, lane, (ep.debug & 128) != 0);
                     if (ep.out32 && !t32 && m < M) {
                         float* o = ep.out32 + (size_t)m * ep.ld32 + nb;
                         if (full_chunk && (ep.ld32 & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.out32) & 31) == 0) {

@@ -342,8 +342,22 @@ __device__ __forceinline__ void load_rows_t(const float* base, int ld, int row0,
 }
 // v: 32 columns of this thread's own row -> fp32 and / or fp16 rows in global memory through the transposed layout
 __device__ __forceinline__ void store_rows_t(const float (&v)[32], float* o32, int ld32, __half* o16, int ld16, int row0, int n_rows,
-                                             int col0, int lane) {
-    if (o16) {
+                                             int col0, int lane, bool transposed16 = false) {
+    if (o16 && !transposed16) {
+        // fp16 rows: one row per lane, two full 32-byte sectors per store.  The transposed form would write 16 bytes
+        // (half a sector) per lane and measured slower (S6 4.8 vs 4.55-4.7 ms/step; attribution: EGX_*_DEBUG bit 128)
+        const int row = row0 + (lane & 3);
+        if (row < n_rows) {
+            uint32_t h[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            stg256(o16 + (size_t)row * ld16 + col0, &h[0]);
+            stg256(o16 + (size_t)row * ld16 + col0 + 16, &h[8]);
+        }
+    } else if (o16) {
         uint32_t h[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
