@@ -1,5 +1,5 @@
 """Condense an ncu CSV (gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch of one
-profiled step) into per-kernel-family totals and profiles/r1_conv_dram.json (DRAM bytes per trunk-conv launch,
+profiled step) into per-kernel-family totals and profiles/r2_conv_dram.json (DRAM bytes per trunk-conv launch,
 read by bench.py for roofline.traffic).  usage: python profiles/conv_dram_from_csv.py launches.csv CLIPS [out.json]"""
 import collections, csv, json, re, sys
 
