@@ -259,3 +259,37 @@ def test_evaluation_loop_matches_the_oracle_composition():
     want = fgd_mod.frechet_distance(fp.mean(0), np.cov(fp, rowvar=False), ft.mean(0), np.cov(ft, rowvar=False))
     assert np.isfinite(out["fgd"]) and abs(out["fgd"] - want) <= 2e-2 * max(abs(want), 1.0)
     assert abs(out["fgd"] - out["fgd_host"]) <= 1e-6 * max(abs(want), 1.0)      # device eigh tail == host numpy tail
+
+
+@pytest.mark.gpu
+def test_emotion_net_and_cvae_at_baseline_batch_sizes():
+    """SURVEY.md §8(d) config 3 (EmotionNet, B = 256) and config 4 (CVAE, 1 M rows) at their full sizes, through
+    size-independent properties: every clip's / row's result equals, bit for bit, what the same clip gives in a small
+    batch (oracle-checked sizes) wherever it sits in the large one, and a sample agrees with the oracle."""
+    m, sd = _big["emotion_net"] if "emotion_net" in _big else build(*CASES["emotion_net"][:2])
+    _big["emotion_net"] = (m, sd)
+    net = m.cuda()
+    g = torch.Generator().manual_seed(5)
+    spec = torch.randn(256, 128, 124, generator=g)
+    with torch.no_grad():
+        big = net(spec.cuda()).cpu()
+        assert torch.isfinite(big).all()
+        for lo in (0, 101, 250):
+            small = net(spec[lo:lo + 6].cuda()).cpu()
+            assert torch.equal(small, big[lo:lo + 6]), f"EmotionNet clips {lo}..: logits depend on the batch"
+        ref = oa.emotion_net(sd, spec[[0, 255]])
+    assert rel_max(big[[0, 255]], ref) <= 2e-3
+    net.cpu()
+    torch.cuda.empty_cache()
+    cv, csd = build(*CASES["cvae"][:2])
+    cv = cv.cuda()
+    n = 1_000_000
+    x, y, eps = (torch.randn(n, k, generator=g) for k in (90, 90, 32))
+    with torch.no_grad():
+        out, mu, lv = cv(x.cuda(), y.cuda(), eps=eps.cuda())
+        for lo in (0, 499_999, n - 300):
+            o2, m2, l2 = cv(x[lo:lo + 300].cuda(), y[lo:lo + 300].cuda(), eps=eps[lo:lo + 300].cuda())
+            assert torch.equal(o2, out[lo:lo + 300]) and torch.equal(m2, mu[lo:lo + 300]) and torch.equal(l2, lv[lo:lo + 300])
+        idx = torch.tensor([0, 123_456, n - 1])
+        r_out, r_mu, r_lv = oa.cvae_forward(csd, x[idx], y[idx], eps[idx])
+    assert rel_max(out[idx].cpu(), r_out) <= 2e-5 and rel_max(mu[idx].cpu(), r_mu) <= 2e-5 and rel_max(lv[idx].cpu(), r_lv) <= 2e-5
