@@ -38,7 +38,9 @@ constexpr int kXBytes = FM * FD * 2;                // 64 KB: 4 k-blocks of 16 K
 constexpr int kHBytes = FM * FH * 2;                // 32 KB: 2 k-blocks of 16 KB
 constexpr int kStageBytes = 32 * 1024;
 constexpr int kFfnStages = 3;
-constexpr int kFfnSmem = kXBytes + 2 * kHBytes + kFfnStages * kStageBytes + 256 + 1024;
+constexpr int kXchBytes = 2 * FM * 2 * 4;          // LayerNorm moment exchange between the two column halves (YW = 2)
+// the dynamic shared-memory array is declared 1024-byte aligned (swizzle atoms), so no slack is reserved for aligning it
+constexpr int kFfnSmem = kXBytes + 2 * kHBytes + kFfnStages * kStageBytes + 256 + kXchBytes;
 
 constexpr int kFfnMaxInner = 2048;
 // By value in the kernel's constant bank (7 KB of parameters): the epilogues index the bias / LayerNorm vectors with
@@ -54,15 +56,20 @@ struct FfnParams {
                                    // hidden-chunk conversion, 4 = no output epilogue work
 };
 
-template <int CL>
+// YW: warp groups of the output epilogue.  1: warps 2-5 / 6-9 convert the even / odd hidden chunks, warps 10-13 run the
+// LayerNorm epilogue.  2: warps 2-5 convert all hidden chunks, warps 6-9 / 10-13 each take one 128-column half of the
+// output rows and exchange their LayerNorm moments through shared memory — the output accumulator, the resource the next
+// tile's second GEMM waits for, is drained twice as fast.
+template <int CL, int YW>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ FfnParams p) {
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     constexpr int kPiece = kStageBytes / CL;          // bytes of a stage one CTA fetches: a {64, 256 / CL} box
     constexpr int kPieceRows = 256 / CL;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
+    if (smem_u32(smem_raw) & 1023u) __trap();
     unsigned char* sX = smem;
     unsigned char* sH = sX + kXBytes;                       // [2][kHBytes]
     unsigned char* ring = sH + 2 * kHBytes;
@@ -78,6 +85,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     uint64_t* y_full = bars + 16;
     uint64_t* y_empty = bars + 17;      // output accumulator read back (4 warps)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+    float* xch = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);      // [half][row][mean, M2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.M + FM - 1) / FM;
@@ -95,7 +103,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             mbar_init(&hacc_full[i], 1); mbar_init(&hacc_empty[i], 4);
             mbar_init(&hs_full[i], 4); mbar_init(&hs_empty[i], 1);
         }
-        mbar_init(y_full, 1); mbar_init(y_empty, 4);
+        mbar_init(y_full, 1); mbar_init(y_empty, 4 * YW);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -231,15 +239,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
 #endif
         }
-    } else if (warp < 10) {
+    } else if (warp < (YW == 2 ? 6 : 10)) {
         // hidden-chunk epilogue: TMEM -> + b1, ReLU, fp16 -> shared memory (SWIZZLE_128B K-major A operand of GEMM2)
-        const int b = (warp - 2) >> 2;                  // chunks j with j & 1 == b
+        const int b0 = YW == 2 ? 0 : (warp - 2) >> 2;   // YW = 1: chunks j with j & 1 == b0; YW = 2: every chunk
         const int q = warp & 3, r = q * 32 + lane;
-        const uint32_t taddr = tmem_H + b * FH + ((uint32_t)(q * 32) << 16);
-        unsigned char* hrow = sH + b * kHBytes + (r >> 3) * 1024 + (r & 7) * 128;
-        uint32_t n = 0;
+        uint32_t n = 0;                                 // uses of buffer b so far = n >> (YW == 2)
         for (int round = 0; round < n_iter; ++round) {
-            for (int j = b; j < NJ; j += 2, ++n) {
+            for (int j = b0; j < NJ; j += (YW == 2 ? 1 : 2), ++n) {
+                const int b = j & 1;
+                const uint32_t taddr = tmem_H + b * FH + ((uint32_t)(q * 32) << 16);
+                unsigned char* hrow = sH + b * kHBytes + (r >> 3) * 1024 + (r & 7) * 128;
+                const uint32_t nb_ = YW == 2 ? n >> 1 : n;
+#define n nb_
                 mbar_wait(&hacc_full[b], n & 1);
                 tc_fence_after();
                 mbar_wait(&hs_empty[b], (n & 1) ^ 1);
@@ -276,6 +287,65 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hs_full[b]);
+#undef n
+            }
+        }
+    } else if (YW == 2) {
+        // output epilogue, split over two warp groups by column half (see YW above)
+        const int half = (warp - 6) >> 2, q = warp & 3, r = q * 32 + lane;
+        const uint32_t taddr = tmem_Y + half * (FD / 2) + ((uint32_t)(q * 32) << 16);
+        const int col_h = half * (FD / 2);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; it < (uint32_t)n_iter; tile += gridDim.x, ++it) {
+            const int row0 = tile * FM + q * 32 + (lane & ~3);
+            uint32_t rn[32];
+            if (tile * FM + r < p.M) {
+                const float* own = p.resid + (size_t)(tile * FM + r) * FD + col_h;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(own + l * 32));
+            }
+            load_rows_t(p.resid, FD, row0, p.M, col_h, lane, rn);
+            mbar_wait(y_full, it & 1);
+            tc_fence_after();
+            float v0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < FD / 64; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                seg_transpose4<8>(rn, lane);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += p.b2[col_h + c * 32 + j] + __uint_as_float(rn[j]);
+                if (c + 1 < FD / 64) load_rows_t(p.resid, FD, row0, p.M, col_h + (c + 1) * 32, lane, rn);
+                if (c == 0) v0 = v[0];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d = v[j] - v0; s1 += d; s2 = fmaf(d, d, s2); }
+                tmem_st32(taddr + c * 32, v);
+            }
+            tmem_st_wait();
+            // moments of this half about its own first value, combined with the other half's (Chan's update, 128 + 128)
+            const float mean_h = v0 + s1 * (2.f / FD), m2_h = fmaxf(s2 - s1 * s1 * (2.f / FD), 0.f);
+            xch[(half * FM + r) * 2] = mean_h;
+            xch[(half * FM + r) * 2 + 1] = m2_h;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float mean_o = xch[((half ^ 1) * FM + r) * 2], m2_o = xch[((half ^ 1) * FM + r) * 2 + 1];
+            const float mean = 0.5f * (mean_h + mean_o);
+            const float dm = mean_h - mean_o;
+            const float rstd = rsqrtf((m2_h + m2_o + dm * dm * (FD / 4)) * (1.f / FD) + 1e-6f);
+#pragma unroll 1
+            for (int c = 0; c < FD / 64; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                if (c == FD / 64 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(y_empty);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    v[j] = fmaf((v[j] - mean) * rstd, p.ln_g[col_h + c * 32 + j], p.ln_b[col_h + c * 32 + j]);
+                store_rows_t(v, p.out32, FD, p.out16, FD, row0, p.M, col_h + c * 32, lane, (p.debug & 128) != 0);
             }
         }
     } else {
@@ -352,8 +422,9 @@ int g_ffn_sms = 0;
 // lock step of a cluster only adds coupling.  What bounds the kernel is the output epilogue (row-per-thread global
 // accesses: 0.9 of the 1.25 ms the six launches take beyond their MMA time).  EGX_FFN_CLUSTER selects 2 / 4 in attribution builds.
 int g_ffn_cluster = 1;
+int g_ffn_yw = 1;          // output-epilogue warp groups (EGX_FFN_YW in attribution builds)
 
-template <int CL>
+template <int CL, int YW>
 int launch_ffn_cl(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMap& t2, const FfnParams& p, int tiles, cudaStream_t s) {
     int grid = tiles < g_ffn_sms ? tiles : g_ffn_sms;
     grid = (grid + CL - 1) / CL * CL;
@@ -364,7 +435,7 @@ int launch_ffn_cl(const CUtensorMap& tx, const CUtensorMap& t1, const CUtensorMa
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ffn_tc_kernel<CL>, tx, t1, t2, p) == cudaSuccess ? 1 : -1;
+    return cudaLaunchKernelEx(&cfg, ffn_tc_kernel<CL, YW>, tx, t1, t2, p) == cudaSuccess ? 1 : -1;
 }
 
 }  // namespace
@@ -374,9 +445,11 @@ int ffn_tc_init_device() {
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&g_ffn_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     g_ffn_cluster = env_switch("EGX_FFN_CLUSTER", g_ffn_cluster);
-    if (cudaFuncSetAttribute(ffn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(ffn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(ffn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
+    g_ffn_yw = env_switch("EGX_FFN_YW", g_ffn_yw);
+    if (cudaFuncSetAttribute(ffn_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ffn_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ffn_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ffn_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -425,9 +498,10 @@ int launch_ffn_tc(const __half* x16, const float* resid, const __half* w1, int l
     }
 #endif
     const int tiles = (M + FM - 1) / FM;
-    if (cl == 4) return launch_ffn_cl<4>(tx, t1, t2, p, tiles, s);
-    if (cl == 2) return launch_ffn_cl<2>(tx, t1, t2, p, tiles, s);
-    return launch_ffn_cl<1>(tx, t1, t2, p, tiles, s);
+    if (cl == 4) return launch_ffn_cl<4, 1>(tx, t1, t2, p, tiles, s);
+    if (cl == 2) return launch_ffn_cl<2, 1>(tx, t1, t2, p, tiles, s);
+    if (g_ffn_yw == 2) return launch_ffn_cl<1, 2>(tx, t1, t2, p, tiles, s);
+    return launch_ffn_cl<1, 1>(tx, t1, t2, p, tiles, s);
 }
 
 }  // namespace egx
