@@ -371,7 +371,7 @@ def run_generator(args, name):
         if world > 1:
             gather_async(d_poses[slot], slot)
 
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, args.steps)
     for _ in range(3):
         e2e_step()
     drain()
@@ -889,7 +889,7 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=32)   # the CPU path is fastest per clip around this batch
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--e2e-chunk", type=int, default=2048)   # measured on one box: 1024 -> 0.93, 2048 -> 0.955 of the device-resident value
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--fgd-variant", default="ted", choices=["ted", "beat"])
     ap.add_argument("--fgd-clips", type=int, default=100_000)
