@@ -72,3 +72,31 @@ def test_frontend_pins_from_the_real_reference(golden_dir):
     fixed = np.stack([ol.make_audio_fixed_length(flat[off[i]:off[i + 1]], 36267) for i in range(len(lens))])
     assert np.array_equal(fixed[:, -64:], g["fixed_tail"])
     assert np.array_equal(fixed.astype(np.float64).sum(axis=1), g["fixed_checksum"])
+
+
+def test_db_pipeline_matches_torchaudio_end_to_end():
+    """F2-F4a as ONE pipeline against an independent implementation: torchaudio's MelSpectrogram (Slaney scale and norm,
+    n_fft 1024, hop 512, centred, zero padded, power 2) + amplitude_to_DB(ref = max, amin 1e-10, top_db 80), which
+    torchaudio documents as the librosa-compatible configuration, in float64.  librosa itself is absent (parity with the
+    reference's offline features stays unpinned); this shows the restatement agrees with a second published
+    implementation of the same recipe."""
+    import torchaudio
+    x = torch.from_numpy(synth.synth_audio(2, 36267, seed=8)).double()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)      # torchaudio builds its window and filterbank in the default dtype
+    try:
+        mel = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=1024, hop_length=512, f_min=0.0,
+                                                   f_max=8000.0, n_mels=128, power=2.0, center=True,
+                                                   pad_mode="constant", norm="slaney", mel_scale="slaney")
+    finally:
+        torch.set_default_dtype(prev)
+    m = mel(x)[..., :70]
+    ref = []
+    for b in range(m.shape[0]):
+        mx = m[b].max()
+        ref.append(torchaudio.functional.amplitude_to_DB(m[b:b + 1], multiplier=10.0, amin=1e-10,
+                                                         db_multiplier=float(torch.log10(torch.clamp(mx, min=1e-10))),
+                                                         top_db=80.0)[0])
+    ref = torch.stack(ref).numpy()
+    got = ol.logmel(x.numpy(), 70, "db", preemph=False)
+    assert np.abs(got - ref).max() <= 1e-8
