@@ -1476,8 +1476,8 @@ int egx_finalize_weights(egx_handle* h) {
     return 0;
 }
 
-int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode, int preemph,
-               float* out, void* stream) {
+static int logmel_checked(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode, int preemph,
+                          float* out, void* stream, bool force_global_tile) {
     if (!h) return 1;
     if (n_clips <= 0) return 0;
     if (n_cols < 1 || n_cols > 1 + n_samples / 512) EGX_FAIL(h, "n_cols out of range for n_samples");
@@ -1487,8 +1487,20 @@ int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, in
         EGX_FAIL(h, "unknown log-mel mode");
     cudaStream_t s = (cudaStream_t)stream;
     StageScope sc(h, 1);
-    LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, s));
+    LAUNCH(h, launch_logmel(h->lm, audio, n_clips, n_samples, n_cols, mode, preemph, out, s, force_global_tile));
     return 0;
+}
+
+int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode, int preemph,
+               float* out, void* stream) {
+    return logmel_checked(h, audio, n_clips, n_samples, n_cols, mode, preemph, out, stream, false);
+}
+
+// Test hook: the same front end through the kernel that keeps the (128, n_cols) tile in global memory (the path of
+// spectrograms wider than 96 columns), whatever the width: the two kernels must agree bit for bit.
+int egx_debug_logmel_global_tile(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode,
+                                 int preemph, float* out, void* stream) {
+    return logmel_checked(h, audio, n_clips, n_samples, n_cols, mode, preemph, out, stream, true);
 }
 
 int egx_audio_fixed_length(egx_handle* h, const float* samples, const int64_t* offsets, int n_clips, int n_out,

@@ -235,7 +235,7 @@ inline int env_switch(const char* name, int dflt) {
 // Kernel launchers (each returns the number of kernels it enqueued, or <0 on launch error)
 // ---------------------------------------------------------------------------------------------
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
-                  int preemph, float* out, cudaStream_t s);
+                  int preemph, float* out, cudaStream_t s, bool force_global_tile = false);
 
 // F5: ragged clips (back to back in `samples`, clip b = [offsets[b], offsets[b+1])) -> (B, N), cropped or symmetric-padded
 int launch_fixed_length(const float* samples, const int64_t* offsets, int B, int N, float* out, cudaStream_t s);

@@ -28,8 +28,10 @@ constexpr int kMels = 128;
 constexpr int kMaxWarps = 12;      // 384 threads x 3 CTAs per SM at <= 56 registers
 constexpr int kBufLen = kHalf + kHalf / 8;     // padded: physical index i + (i >> 3)
 
+// Every multiply-add below is spelled out (fmaf / __fmul_rn): left to the compiler, which product of a*b - c*d is fused
+// is decided per call site, and the two kernels of this file must agree bit for bit.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(fmaf(a.x, b.x, -__fmul_rn(a.y, b.y)), fmaf(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -54,13 +56,15 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
     const float2 b4 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]), b6 = cadd(a[3], a[7]), b7 = mul_mi(csub(a[3], a[7]));
     const float2 c0 = cadd(b0, b2), c1 = cadd(b1, b3), c2 = csub(b0, b2), c3 = csub(b1, b3);
     const float2 c4 = cadd(b4, b6), o1 = cadd(b5, b7), o2 = csub(b4, b6), o3 = csub(b5, b7);
-    const float2 c5 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));     // * (1 - i)/sqrt2
     const float2 c6 = mul_mi(o2);                                            // * (-i)
-    const float2 c7 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));    // * (-1 - i)/sqrt2
+    // odd outputs 1/5 and 3/7: c + W8 o and c - W8 o with W8 = (1 - i)/sqrt2, (-1 - i)/sqrt2 — explicit fused forms
+    const float s5x = o1.x + o1.y, s5y = o1.y - o1.x, s7x = o3.y - o3.x, s7y = o3.x + o3.y;
     a[0] = cadd(c0, c4); a[4] = csub(c0, c4);
-    a[1] = cadd(c1, c5); a[5] = csub(c1, c5);
+    a[1] = make_float2(fmaf(h, s5x, c1.x), fmaf(h, s5y, c1.y));
+    a[5] = make_float2(fmaf(-h, s5x, c1.x), fmaf(-h, s5y, c1.y));
     a[2] = cadd(c2, c6); a[6] = csub(c2, c6);
-    a[3] = cadd(c3, c7); a[7] = csub(c3, c7);
+    a[3] = make_float2(fmaf(h, s7x, c3.x), fmaf(-h, s7y, c3.y));
+    a[7] = make_float2(fmaf(-h, s7x, c3.x), fmaf(h, s7y, c3.y));
 }
 
 // One Stockham radix-8 pass of the warp's 512-point FFT, in place: every lane reads the 16 points of its two
@@ -147,13 +151,13 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
                 float xm = __shfl_up_sync(0xffffffffu, r1[ii], 1);
                 if (lane == 0) xm = i ? carry : ((s0 - 1 >= 0 && s0 - 1 < N) ? __ldg(x + s0 - 1) : 0.f);
                 carry = __shfl_sync(0xffffffffu, r1[ii], 31);
-                const float y1 = x1 - 0.97f * x0;
-                const float y0 = x0 - 0.97f * (s0 == 0 ? r1[ii] : xm);
+                const float y1 = fmaf(-0.97f, x0, x1);
+                const float y0 = fmaf(-0.97f, s0 == 0 ? r1[ii] : xm, x0);
                 x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? y1 : 0.f;
                 x0 = (s0 >= 0 && s0 < N) ? y0 : 0.f;
             }
             const float2 w = __ldg(reinterpret_cast<const float2*>(window + 2 * n));
-            buf[pad(n)] = make_float2(x0 * w.x, x1 * w.y);
+            buf[pad(n)] = make_float2(__fmul_rn(x0, w.x), __fmul_rn(x1, w.y));
         }
         }
         __syncwarp();
@@ -174,7 +178,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
                 const float2 od = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
                 const float2 r = cmul(od, __ldg(&tw1024[k]));
                 const float re = ev.x + r.x, im = ev.y + r.y;
-                pw[i] = re * re + im * im;
+                pw[i] = fmaf(re, re, __fmul_rn(im, im));
             }
         }
         __syncwarp();
@@ -210,7 +214,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
             for (int t = lane; t < n_cols; t += 32) s += row[t];
             const float mean = warp_sum(s) / n_cols;
             float q = 0.f;
-            for (int t = lane; t < n_cols; t += 32) { const float d = row[t] - mean; q += d * d; }
+            for (int t = lane; t < n_cols; t += 32) { const float d = row[t] - mean; q = fmaf(d, d, q); }
             const float rstd = rsqrtf(warp_sum(q) / n_cols + 1e-5f);
             for (int t = lane; t < n_cols; t += 32) o[m * n_cols + t] = (row[t] - mean) * rstd;
         }
@@ -229,6 +233,223 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
             const float v = fmaxf(tile[i] - mx, -80.f);
             o[i] = f16_round ? __half2float(__float2half_rn(v)) : v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Round-2 variant for tiles that fit in shared memory next to the FFT buffers (n_cols <= kTileMaxCols): the SAME
+// arithmetic in the same order (bit-identical output), restructured around what bounded the kernel above — the L1/shared
+// pipe (82% busy: 658 shared wavefronts + 437 global tag requests per frame) —
+//   * the frame goes from global memory straight into the registers of the first radix-8 pass (no staging round trip);
+//     interior frames (68 of 71 for a TED clip) skip every bounds check;
+//   * the buffer index is XOR-swizzled (i ^ ((i >> 3) & 15)): conflict-free for the stride-8 / stride-64 writes AND the
+//     unit-stride reads (the padded layout made every read a 2-way conflict), and needs no padding;
+//   * the last pass stays in registers and the real-FFT untangling fetches its mirror bin Z[512 - k] from the lane
+//     that holds it with two shuffles instead of a store + two loads;
+//   * the (128, n_cols) tile lives in shared memory: the transposed per-frame writes (32 lines per store) and the two
+//     re-reads for the statistics never leave the SM, the normalised tile is written once, coalesced.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTileMaxCols = 96;
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 15); }
+
+// one complex point (two samples) of a frame with every check of the general path
+__device__ __forceinline__ float2 load_point_checked(const float* __restrict__ x, int N, int s0, int preemph) {
+    float x0 = (s0 >= 0 && s0 < N) ? __ldg(x + s0) : 0.f;
+    float x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? __ldg(x + s0 + 1) : 0.f;
+    if (preemph) {
+        const float xm = s0 == 0 ? x1 : ((s0 - 1 >= 0 && s0 - 1 < N) ? __ldg(x + s0 - 1) : 0.f);
+        const float y1 = fmaf(-0.97f, x0, x1);
+        const float y0 = fmaf(-0.97f, xm, x0);
+        x1 = (s0 + 1 >= 0 && s0 + 1 < N) ? y1 : 0.f;
+        x0 = (s0 >= 0 && s0 < N) ? y0 : 0.f;
+    }
+    return make_float2(x0, x1);
+}
+
+// one radix-8 pass with the inputs already in registers: twiddle, butterflies
+template <int NS>
+__device__ __forceinline__ void twiddle_dft8(float2 (&a)[8], int j, const float2* __restrict__ tw512) {
+    if (NS > 1) {
+#pragma unroll
+        for (int t = 1; t < 8; ++t) a[t] = cmul(a[t], __ldg(&tw512[((NS == 8 ? 0 : 8) + t) * 64 + j]));
+    }
+    dft8(a);
+}
+
+__global__ void __launch_bounds__(kMaxWarps * 32, 2)
+logmel_tile_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int preemph,
+                   float* __restrict__ out, const float* __restrict__ window,
+                   const float2* __restrict__ tw512, const float2* __restrict__ tw1024,
+                   const int* __restrict__ mel_start, const int* __restrict__ mel_ptr,
+                   const float* __restrict__ mel_w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* fftbuf = reinterpret_cast<float2*>(smem_raw);                          // [warps][kHalf + 8]
+    __shared__ float s_red[kMaxWarps];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    constexpr int kBuf = kHalf + 8;                                                // 513 power values fit
+    float* stile = reinterpret_cast<float*>(fftbuf + n_warps * kBuf);               // [kMels][pitch], pitch odd
+    const int pitch = n_cols | 1;
+    const bool log_in = (mode & 0xff) == EGX_LOGMEL_LOG_IN, f16_round = (mode & EGX_LOGMEL_FP16_STORAGE) != 0;
+    const float* x = audio + (size_t)blockIdx.x * N;
+    float2* buf = fftbuf + warp * kBuf;
+    // the clip's first sample sits on an even float of the address space (8-byte loads of sample pairs); uniform per CTA
+    const bool aligned = (((reinterpret_cast<uintptr_t>(audio) >> 2) + (size_t)blockIdx.x * N) & 1) == 0;
+
+    for (int t = warp; t < n_cols; t += n_warps) {
+        const int base = t * kHop - kFFT / 2;
+        // interior frame: every sample (and the one before the frame) exists, and no sample is the clip's first.  A clip
+        // that starts on an odd float (N odd: every other clip) reads the aligned pairs (s0 - 1, s0), (s0 + 1, s0 + 2):
+        // the first carries the pre-emphasis neighbour, the second touches one sample past the frame
+        const bool interior = base >= 2 && base + kFFT + (aligned ? 0 : 1) <= N;
+        float2 a[2][8];
+        // ---- framing + pre-emphasis + window -> registers of pass 1 (point n = j + 64 tt, j = lane + 32 h2), pass 1 ----
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = lane + 32 * h2;
+            if (interior && aligned) {
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) a[h2][tt] = __ldg(reinterpret_cast<const float2*>(x + base + 2 * (j + 64 * tt)));
+                if (preemph) {
+#pragma unroll
+                    for (int tt = 0; tt < 8; ++tt) {
+                        // x[s0 - 1] is the odd sample of the previous point: the neighbouring lane has it
+                        float xm = __shfl_up_sync(0xffffffffu, a[h2][tt].y, 1);
+                        if (lane == 0) xm = __ldg(x + base + 2 * (j + 64 * tt) - 1);
+                        const float y1 = fmaf(-0.97f, a[h2][tt].x, a[h2][tt].y);
+                        const float y0 = fmaf(-0.97f, xm, a[h2][tt].x);
+                        a[h2][tt] = make_float2(y0, y1);
+                    }
+                }
+            } else if (interior) {
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) {
+                    const float* ps = x + base + 2 * (j + 64 * tt);
+                    const float2 lo = __ldg(reinterpret_cast<const float2*>(ps - 1));
+                    const float2 hi = __ldg(reinterpret_cast<const float2*>(ps + 1));
+                    if (preemph) {
+                        const float y1 = fmaf(-0.97f, lo.y, hi.x);
+                        const float y0 = fmaf(-0.97f, lo.x, lo.y);
+                        a[h2][tt] = make_float2(y0, y1);
+                    } else {
+                        a[h2][tt] = make_float2(lo.y, hi.x);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) a[h2][tt] = load_point_checked(x, N, base + 2 * (j + 64 * tt), preemph);
+            }
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                const float2 w = __ldg(reinterpret_cast<const float2*>(window + 2 * (j + 64 * tt)));
+                a[h2][tt] = make_float2(__fmul_rn(a[h2][tt].x, w.x), __fmul_rn(a[h2][tt].y, w.y));
+            }
+            dft8(a[h2]);
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) buf[swz(j * 8 + tt)] = a[h2][tt];        // NS = 1: out[(j - 0) * 8 + 0 + tt]
+        }
+        __syncwarp();
+        // ---- pass 2 (NS = 8) ----
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = lane + 32 * h2;
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) a[h2][tt] = buf[swz(j + 64 * tt)];
+            twiddle_dft8<8>(a[h2], j, tw512);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = lane + 32 * h2, k = j & 7;
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) buf[swz((j - k) * 8 + k + tt * 8)] = a[h2][tt];
+        }
+        __syncwarp();
+        // ---- pass 3 (NS = 64): lane holds Z[j + 64 tt] afterwards ----
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int j = lane + 32 * h2;
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) a[h2][tt] = buf[swz(j + 64 * tt)];
+            twiddle_dft8<64>(a[h2], j, tw512);
+        }
+        __syncwarp();                                   // every lane has read its inputs: the buffer becomes `power`
+        // ---- untangle to the real spectrum: bin k = j + 64 tt needs Z[512 - k] = Z[(64 - j) + 64 (7 - tt)], held by lane
+        //      (32 - lane) & 31 in the other half (lane 0: see below) ----
+        float* power = reinterpret_cast<float*>(buf);
+        const int src = (32 - lane) & 31;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) {
+                // what this lane must OFFER: lanes 1..31 their element (other half, 7 - tt); lane 0 is its own source and
+                // needs Z[64 (8 - tt)] (h2 = 0) or Z[32 + 64 (7 - tt)] (h2 = 1)
+                const float2 other = a[h2 ^ 1][7 - tt];
+                const float2 self0 = h2 == 0 ? a[0][(8 - tt) & 7] : a[1][7 - tt];
+                const float2 offer = lane == 0 ? self0 : other;
+                float2 zn;
+                zn.x = __shfl_sync(0xffffffffu, offer.x, src);
+                zn.y = __shfl_sync(0xffffffffu, offer.y, src);
+                const float2 zk = a[h2][tt];
+                const int k = lane + 32 * h2 + 64 * tt;
+                const float2 ev = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                const float2 od = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+                const float2 r = cmul(od, __ldg(&tw1024[k]));
+                const float re = ev.x + r.x, im = ev.y + r.y;
+                power[k] = fmaf(re, re, __fmul_rn(im, im));
+            }
+        }
+        if (lane == 0) {                                // bin 512: zk = zn = Z[0]
+            const float2 z0 = a[0][0];
+            const float2 ev = make_float2(0.5f * (z0.x + z0.x), 0.5f * (z0.y - z0.y));
+            const float2 od = make_float2(0.5f * (z0.y + z0.y), -0.5f * (z0.x - z0.x));
+            const float2 r = cmul(od, __ldg(&tw1024[kHalf]));
+            const float re = ev.x + r.x, im = ev.y + r.y;
+            power[kHalf] = fmaf(re, re, __fmul_rn(im, im));
+        }
+        __syncwarp();
+        // ---- sparse mel projection + log ----
+#pragma unroll
+        for (int mm = 0; mm < kMels / 32; ++mm) {
+            const int m = lane + 32 * mm;
+            const int nt = mel_ptr[m], b0 = mel_start[m];
+            float acc = 0.f;
+            for (int p = 0; p < nt; ++p) acc = fmaf(__ldg(mel_w + p * kMels + m), power[b0 + p], acc);
+            float v;
+            if (log_in) v = logf(acc + 1e-6f);
+            else v = 10.f * log10f(fmaxf(acc, 1e-10f));
+            stile[m * pitch + t] = v;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    float* o = out + (size_t)blockIdx.x * kMels * n_cols;
+    if (log_in) {
+        for (int m = warp; m < kMels; m += n_warps) {
+            const float* row = stile + m * pitch;
+            float s = 0.f;
+            for (int t = lane; t < n_cols; t += 32) s += row[t];
+            const float mean = warp_sum(s) / n_cols;
+            float q = 0.f;
+            for (int t = lane; t < n_cols; t += 32) { const float d = row[t] - mean; q = fmaf(d, d, q); }
+            const float rstd = rsqrtf(warp_sum(q) / n_cols + 1e-5f);
+            for (int t = lane; t < n_cols; t += 32) o[m * n_cols + t] = (row[t] - mean) * rstd;
+        }
+    } else {
+        float mx = -INFINITY;
+        for (int m = warp; m < kMels; m += n_warps)
+            for (int t = lane; t < n_cols; t += 32) mx = fmaxf(mx, stile[m * pitch + t]);
+        mx = warp_max(mx);
+        if (lane == 0) s_red[warp] = mx;
+        __syncthreads();
+        mx = s_red[0];
+        for (int w = 1; w < n_warps; ++w) mx = fmaxf(mx, s_red[w]);
+        for (int m = warp; m < kMels; m += n_warps)
+            for (int t = lane; t < n_cols; t += 32) {
+                const float v = fmaxf(stile[m * pitch + t] - mx, -80.f);
+                o[m * n_cols + t] = f16_round ? __half2float(__float2half_rn(v)) : v;
+            }
     }
 }
 
@@ -252,25 +473,34 @@ __global__ void fixed_length_kernel(const float* __restrict__ samples, const int
 
 }  // namespace
 
+int g_logmel_tile = 1;     // EGX_LOGMEL_TILE (attribution builds): 0 = the global-tile kernel for every width
+
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
-                  int preemph, float* out, cudaStream_t s) {
+                  int preemph, float* out, cudaStream_t s, bool force_global_tile) {
     // warps per CTA: the count in [9, 12] that wastes the fewest warp slots in the last round of frames
     int warps = kMaxWarps;
     for (int w = kMaxWarps; w >= 9; --w)
         if ((n_cols + w - 1) / w * w < (n_cols + warps - 1) / warps * warps) warps = w;
-    const size_t smem = sizeof(float2) * warps * kBufLen;
+    const bool tile = !force_global_tile && env_switch("EGX_LOGMEL_TILE", g_logmel_tile) && n_cols <= kTileMaxCols;
+    const size_t smem = tile ? sizeof(float2) * warps * (kHalf + 8) + sizeof(float) * kMels * (size_t)(n_cols | 1)
+                             : sizeof(float2) * warps * kBufLen;
     // opt-in shared-memory size is a per-device function attribute (one handle per device may live in one process)
-    static size_t configured[64] = {};
+    static size_t configured[2][64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-    if (smem > configured[dev]) {
-        if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) return -1;
-        configured[dev] = smem;
+    if (smem > configured[tile][dev]) {
+        const cudaError_t e = tile ? cudaFuncSetAttribute(logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        configured[tile][dev] = smem;
     }
-    logmel_kernel<<<B, warps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window,
-                                                t.tw512, t.tw1024, t.mel_start, t.mel_ptr,
-                                                t.mel_w);
+    if (tile)
+        logmel_tile_kernel<<<B, warps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window, t.tw512, t.tw1024,
+                                                       t.mel_start, t.mel_ptr, t.mel_w);
+    else
+        logmel_kernel<<<B, warps * 32, smem, s>>>(audio, N, n_cols, mode, preemph, out, t.window,
+                                                    t.tw512, t.tw1024, t.mel_start, t.mel_ptr,
+                                                    t.mel_w);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

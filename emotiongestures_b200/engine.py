@@ -133,7 +133,7 @@ class Engine:
                                                         self._stream()), "egx_audio_fixed_length")
         return out
 
-    def logmel(self, audio, mode: int = LOGMEL_REFERENCE, preemph: bool = False, n_cols=None):
+    def logmel(self, audio, mode: int = LOGMEL_REFERENCE, preemph: bool = False, n_cols=None, _global_tile=False):
         """(B,N) 16 kHz audio -> (B,128,n_cols) log-mel (F1–F4).  Defaults = the reference's live features
         (config.LOGMEL_REFERENCE); the north star's PreEmphasis + log + InstanceNorm recipe is
         `mode=LOGMEL_LOG_IN, preemph=True`."""
@@ -144,8 +144,8 @@ class Engine:
         n_cols = self.cfg.spec_w if n_cols is None else int(n_cols)
         out = torch.empty((b, self.cfg.n_mels, n_cols), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            self._check(self.lib.egx_logmel(self._h, _ptr(a), b, n, n_cols, int(mode),
-                                            int(bool(preemph)), _ptr(out), self._stream()),
+            fn = self.lib.egx_debug_logmel_global_tile if _global_tile else self.lib.egx_logmel   # test hook
+            self._check(fn(self._h, _ptr(a), b, n, n_cols, int(mode), int(bool(preemph)), _ptr(out), self._stream()),
                         "egx_logmel")
         return out
 

@@ -212,6 +212,12 @@ EGX_API int  egx_debug_ffn_tc(egx_handle* h, const float* x, const float* w1, co
                       const float* b2, const float* ln_g, const float* ln_b, int M, int d_inner, float* out32,
                       void* out16, void* stream);
 
+/* Test hook of the front end: egx_logmel through the kernel that keeps the (128, n_cols) tile in global memory (the
+ * path of spectrograms wider than 96 columns) whatever the width.  Both kernels run the same arithmetic in the same
+ * order: tests require bit-identical outputs. */
+EGX_API int  egx_debug_logmel_global_tile(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols,
+                                  int mode, int preemph, float* out, void* stream);
+
 /* Parity probe of the tcgen05 implicit-GEMM convolution alone.  in16: NHWC fp16 (B,H,W,cin); w16: fp16
  * [cout][ks*ks][cin]; y = (relu_first ? relu(acc+bias) : acc+bias)*scale + shift; out16: NHWC fp16, or
  * (B,cout,Ho*Wo) fp16 when nchw != 0; se_part (nullable): [B][tiles][cout] per-tile channel sums. */

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from emotiongestures_b200 import BEAT, LOGMEL_DB, LOGMEL_LOG_IN, TED
+from emotiongestures_b200 import BEAT, LOGMEL_DB, LOGMEL_LOG_IN, LOGMEL_REFERENCE, TED
 from oracle import generator as og
 from oracle import logmel as ol
 from oracle import synth
@@ -83,6 +83,25 @@ def test_logmel_no_preemph_and_ragged_cols():
         assert np.abs(got - ref).max() <= 1e-4
     with pytest.raises(RuntimeError):
         eng.logmel(torch.from_numpy(audio), LOGMEL_DB, False, n_cols=11)
+
+
+@pytest.mark.parametrize("mode,preemph", [(LOGMEL_LOG_IN, True), (LOGMEL_LOG_IN, False), (LOGMEL_DB, False),
+                                          (LOGMEL_REFERENCE, False), (LOGMEL_DB, True)])
+def test_logmel_tile_kernels_agree_bitwise(mode, preemph):
+    """K1 has two kernels (tile in shared memory for n_cols <= 96, tile in global memory above): same arithmetic in the same
+    order, so identical bits — for even and odd clip starts (N odd: every other clip is misaligned for 8-byte loads),
+    clips shorter than a frame, ragged widths, and a batch view that starts on an odd float."""
+    eng, _ = _engine("ted", 0, "fp32")
+    for n, cols, b in ((36267, 70, 5), (36268, 70, 3), (5000, 7, 4), (700, 2, 3), (36267, 1, 2), (48000, 94, 2)):
+        audio = torch.from_numpy(synth.synth_audio(b, n, seed=n % 97)).cuda()
+        a = eng.logmel(audio, mode, preemph, n_cols=cols)
+        g = eng.logmel(audio, mode, preemph, n_cols=cols, _global_tile=True)
+        assert torch.equal(a, g), (n, cols)
+    flat = torch.from_numpy(synth.synth_audio(1, 3 * 36267 + 1, seed=5)).cuda().reshape(-1)
+    odd = flat[1:].reshape(3, 36267)                      # contiguous view whose first sample is on an odd float
+    assert odd.data_ptr() % 8 == 4
+    assert torch.equal(eng.logmel(odd, mode, preemph, n_cols=70), eng.logmel(odd, mode, preemph, n_cols=70, _global_tile=True))
+    assert torch.equal(eng.logmel(odd, mode, preemph, n_cols=70), eng.logmel(odd.clone(), mode, preemph, n_cols=70))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
