@@ -367,18 +367,20 @@ def run_generator(args, name):
             torch.cuda.current_stream(dev).wait_event(free[slot])
         # public API: pinned host in -> pinned host out, chunked so PCIe copies overlap the kernels
         eng.infer_host(h_audio, h_prior, h_poses, chunk=args.e2e_chunk, mode=LOGMEL_LOG_IN, preemph=True,
-                       poses_dev=d_poses[slot])
+                       poses_dev=d_poses[slot], join=False)
         if world > 1:
             gather_async(d_poses[slot], slot)
 
     e2e_steps = max(3, args.steps)
     for _ in range(3):
         e2e_step()
+    eng.host_join()
     drain()
     d.sync()
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
+    eng.host_join()          # every step's poses are in host memory before the closing event
     drain()
     e1.record()
     d.sync()
@@ -540,7 +542,9 @@ def run_generator(args, name):
                           "l2": "inputs larger than L2 (%.0f MB audio per step)" % (audio.numel() * 4 / 1e6)})
         line.update({
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "Engine.infer_host (pinned host in/out, %d-clip chunks, copies overlapped)" % args.e2e_chunk},
+                    "api": "Engine.infer_host(join=False) per step + host_join() before the closing event: pinned host in/out, %d-clip "
+                           "chunks, every copy inside the timed region, overlapped with the kernels of the neighbouring chunk / step"
+                           % args.e2e_chunk},
             "gpu_launches": launches, "roofline": roofline, "stages": per_stage, "cpu_baseline": cpu, "parity": parity,
             "strong_scaling": strong, "collectives": collectives, "fgd": fgd_leg, "small_batch_latency": small,
             "clocks": clocks})
@@ -889,7 +893,10 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=32)   # the CPU path is fastest per clip around this batch
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=2048)   # measured on one box: 1024 -> 0.93, 2048 -> 0.955 of the device-resident value
+    # clips per pipeline chunk of Engine.infer_host.  Measured on one box against the device-resident value: 1024 -> 0.93,
+    # 2048 -> 0.965, 4096 (= the whole step: step k+1's host->device copy runs under step k's kernels, step k's
+    # device->host copy under step k+1's) -> 0.995
+    ap.add_argument("--e2e-chunk", type=int, default=4096)
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--fgd-variant", default="ted", choices=["ted", "beat"])
     ap.add_argument("--fgd-clips", type=int, default=100_000)

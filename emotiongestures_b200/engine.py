@@ -184,13 +184,16 @@ class Engine:
         return poses, emo, sem, logits
 
     def infer_host(self, audio_h, prior_h, poses_h, chunk: int = 512, mode: int = LOGMEL_REFERENCE,
-                   preemph: bool = False, poses_dev=None):
+                   preemph: bool = False, poses_dev=None, join: bool = True):
         """End-to-end batch from PINNED host buffers: audio_h (B,N), prior_h (B,p,P) -> poses_h (B,F,P).
 
         The batch is cut into chunks; the host->device copy of chunk i+1, the kernels of chunk i and
         the device->host copy of chunk i-1 run on three streams, so PCIe time hides behind compute.
         `poses_dev` (optional, (B,F,P) device tensor) also keeps the poses on the GPU (pose gather).
         Returns after enqueueing; the caller synchronises (torch.cuda.synchronize / an event).
+        `join=True` makes the CURRENT stream wait for the last device->host copy, so synchronising that stream is
+        enough; a caller that streams batch after batch passes `join=False` (the next call's kernels then do not queue
+        behind this call's last copy) and calls `host_join()` once before it reads the host buffers.
         """
         cfg, dev = self.cfg, self.device
         b = audio_h.shape[0]
@@ -251,8 +254,15 @@ class Engine:
                 st["out_free"][slot].record(st["d2h"])
             used[slot] = True
         st["next_slot"] = (st.get("next_slot", 0) + len(bounds)) & 1
-        main.wait_stream(st["d2h"])
+        if join:
+            main.wait_stream(st["d2h"])
         return poses_h
+
+    def host_join(self):
+        """Make the current stream wait for every device->host copy `infer_host(join=False)` has enqueued."""
+        st = getattr(self, "_pipe", None)
+        if st is not None:
+            torch.cuda.current_stream(self.device).wait_stream(st["d2h"])
 
     def _infer_host_whole(self, audio_h, prior_h, poses_h, mode, preemph, poses_dev):
         dev = self.device
