@@ -140,7 +140,11 @@ class Dist:
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.numa_node = None
         if self.world > 1:
+            # one process per GPU: keep this rank's pinned buffers on the GPU's own NUMA node
+            from emotiongestures_b200.sharding import bind_host_to_gpu_node
+            self.numa_node = bind_host_to_gpu_node(self.local)
             dist.init_process_group("nccl", device_id=self.dev)
 
     def sync(self):
@@ -539,7 +543,8 @@ def run_generator(args, name):
                          {"workload": spec_["workload"], "clips_per_gpu": B, "global_batch": B * world,
                           "precision": args.precision, "logmel": "preemph+log+InstanceNorm (F4b)",
                           "parallelism": f"dp{world} (clip-sharded; pose all_gather_into_tensor on a side stream)",
-                          "l2": "inputs larger than L2 (%.0f MB audio per step)" % (audio.numel() * 4 / 1e6)})
+                          "l2": "inputs larger than L2 (%.0f MB audio per step)" % (audio.numel() * 4 / 1e6),
+                          "host_numa_node_rank0": d.numa_node})
         line.update({
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "Engine.infer_host(join=False) per step + host_join() before the closing event: pinned host in/out, %d-clip "

@@ -47,3 +47,34 @@ def all_gather_poses(local: torch.Tensor, n_clips: int, group=None) -> torch.Ten
     dist.all_gather_into_tensor(out, send.contiguous(), group=group)
     parts = [out[r * biggest: r * biggest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
     return torch.cat(parts, dim=0)
+
+
+def bind_host_to_gpu_node(device_index: int):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated
+    afterwards (first-touch placement) sit next to that GPU's PCIe root: with one process per GPU streaming ~600 MB per
+    step each, cross-socket copies otherwise share the inter-socket link.  Best effort: returns the node number, or
+    None when the topology cannot be read (containers without /sys PCI entries, single-node hosts) — never raises."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+

@@ -168,3 +168,13 @@ def test_dropin_reads_the_geometry_of_the_real_reference_modules():
         with pytest.raises(RuntimeError, match="sm_100a CUDA devices only"):
             install(torch.nn.DataParallel(ref) if chunk else ref)
         assert type(ref) is cls
+
+
+def test_bind_host_to_gpu_node_is_best_effort():
+    """No GPU / no PCI topology: the helper reports None and leaves the affinity alone."""
+    import os
+    from emotiongestures_b200.sharding import bind_host_to_gpu_node
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert bind_host_to_gpu_node(0) is None
+        assert os.sched_getaffinity(0) == before
