@@ -975,7 +975,7 @@ int g_debug = 0;
 int g_raster = 1;       // EGX_CONV_RASTER (attribution builds) bits: 1 = raster tiles for the 64 / 128-channel halo kernels, 2 = 32-channel
 int g_out_direct = 1;   // EGX_CONV_OUT bit 0: 32->32 halo kernel stores straight from registers, bit 1: 64->64 too, bit 2: 64->64 gated
 int g_contig = 0;    // EGX_CONV_CONTIG: 1 = contiguous tile runs per CTA, 0 = strided walk (default: measured faster, the CTAs share halos in L2)
-int g_halo = 7;       // EGX_CONV_HALO bits: 1 = 64->64 convs, 2 = 32->32, 4 = 128->128, 8 = final conv (128 -> <= 48, NCHW out)
+int g_halo = 15;      // EGX_CONV_HALO bits: 1 = 64->64 convs, 2 = 32->32, 4 = 128->128, 8 = final conv (128 -> <= 48, NCHW out)
 
 template <int CIN, int NPAD, int TAPS, bool HALO, int OUT, int MODE>
 int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half* out, float* se_part, int n_off, cudaStream_t s,
