@@ -997,6 +997,12 @@ int launch_one(const ConvW& c, const __half* in, int B, int Hin, int Win, __half
         int mw, rows;
         if (HALO && OUT != OUT_NCHW && CIN == NPAD && CIN <= 64 && use_raster_fwd(CIN, p.Ho, p.Wo) && raster_geometry(CIN, p.Ho, p.Wo, &mw, &rows))
             set_raster(p, B, mw, rows);
+        if (HALO && OUT == OUT_NCHW && use_raster_fwd(CIN, p.Ho, p.Wo)) {
+            // final conv (128 -> 34 frames): raster tiles when two stages of whole-row patches fit beside the weights
+            mw = p.Wo + 2; rows = raster_map_rows(mw);
+            const int patch = (rows * mw * S::kSwz + 1023) / 1024 * 1024;
+            if (mw <= 256 && rows <= 256 && 2 * S::kChunks * patch <= S::kRingBytes) set_raster(p, B, mw, rows);
+        }
     }
     // rows a tap-shifted 128-row operand can reach: the whole box, and (patch tiles) 128 + 2 MW + 2 rows from its start
     p.patch_bytes = HALO ? (std::max(p.MW * (p.BH + 2), p.raster ? 0 : 128 + 2 * p.MW + 2) * S::kSwz + 1023) / 1024 * 1024
