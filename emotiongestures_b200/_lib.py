@@ -31,6 +31,7 @@ PROTOTYPES = {
                              C.c_void_p, C.c_void_p]),
     "egx_debug_logmel_global_tile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p, C.c_void_p]),
+    "egx_audio_pcm16_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "egx_audio_fixed_length": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "egx_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "egx_generator_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -1503,6 +1503,16 @@ int egx_debug_logmel_global_tile(egx_handle* h, const float* audio, int n_clips,
     return logmel_checked(h, audio, n_clips, n_samples, n_cols, mode, preemph, out, stream, true);
 }
 
+int egx_audio_pcm16_to_f32(egx_handle* h, const int16_t* pcm, int64_t n_samples, float* out, void* stream) {
+    if (!h) return 1;
+    if (n_samples <= 0) return 0;
+    if (!pcm || !out) EGX_FAIL(h, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    StageScope sc(h, 1);
+    LAUNCH(h, launch_pcm16_to_f32(pcm, n_samples, out, s));
+    return 0;
+}
+
 int egx_audio_fixed_length(egx_handle* h, const float* samples, const int64_t* offsets, int n_clips, int n_out,
                            float* out, void* stream) {
     if (!h) return 1;

@@ -237,6 +237,8 @@ inline int env_switch(const char* name, int dflt) {
 int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n_cols, int mode,
                   int preemph, float* out, cudaStream_t s, bool force_global_tile = false);
 
+int launch_pcm16_to_f32(const int16_t* in, int64_t n, float* out, cudaStream_t s);
+
 // F5: ragged clips (back to back in `samples`, clip b = [offsets[b], offsets[b+1])) -> (B, N), cropped or symmetric-padded
 int launch_fixed_length(const float* samples, const int64_t* offsets, int B, int N, float* out, cudaStream_t s);
 

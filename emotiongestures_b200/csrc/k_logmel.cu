@@ -471,7 +471,21 @@ __global__ void fixed_length_kernel(const float* __restrict__ samples, const int
     }
 }
 
+// 16-bit PCM -> float in [-1, 1): x / 32768, exact — the scaling every wav decoder applies; done on the device so that
+// the host->device copy of raw speech carries 2 bytes per sample instead of 4 (extension, see include/egx.h).
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ in, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (float)in[i] * (1.f / 32768.f);
+}
+
 }  // namespace
+
+int launch_pcm16_to_f32(const int16_t* in, int64_t n, float* out, cudaStream_t s) {
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    pcm16_to_f32_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>(in, n, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
 int g_logmel_tile = 1;     // EGX_LOGMEL_TILE (attribution builds): 0 = the global-tile kernel for every width
 

@@ -133,6 +133,17 @@ class Engine:
                                                         self._stream()), "egx_audio_fixed_length")
         return out
 
+    def pcm16_to_float(self, pcm, out=None):
+        """int16 PCM device tensor -> float32 in [-1, 1) (x / 32768, exact), on the device (`egx_audio_pcm16_to_f32`)."""
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
+            raise RuntimeError("pcm must be a contiguous int16 CUDA tensor")
+        if out is None:
+            out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.egx_audio_pcm16_to_f32(self._h, _ptr(pcm), pcm.numel(), _ptr(out), self._stream()),
+                        "egx_audio_pcm16_to_f32")
+        return out
+
     def logmel(self, audio, mode: int = LOGMEL_REFERENCE, preemph: bool = False, n_cols=None, _global_tile=False):
         """(B,N) 16 kHz audio -> (B,128,n_cols) log-mel (F1–F4).  Defaults = the reference's live features
         (config.LOGMEL_REFERENCE); the north star's PreEmphasis + log + InstanceNorm recipe is
@@ -199,17 +210,21 @@ class Engine:
         b = audio_h.shape[0]
         if not (audio_h.is_pinned() and prior_h.is_pinned() and poses_h.is_pinned()):
             raise RuntimeError("infer_host needs pinned host tensors (torch.Tensor.pin_memory())")
+        pcm = audio_h.dtype == torch.int16
+        if not pcm and audio_h.dtype != torch.float32:
+            raise RuntimeError("audio_h must be float32 or int16 PCM")
         if self.batch_coupled and b > 0:
             # Prior_MemoryEncoder multiplies by memory_encoding.t() @ pred_encoding, a sum over the clips of the call
             # (Full_model/Models_memory.py:287-288): cutting the batch would change every clip's poses.  The whole
             # batch goes through as ONE forward — same result as forward() on it — and only the copies are chunked.
             return self._infer_host_whole(audio_h, prior_h, poses_h, mode, preemph, poses_dev)
         st = getattr(self, "_pipe", None)
-        if st is None or st["chunk"] < min(chunk, b):
+        if st is None or st["chunk"] < min(chunk, b) or st["pcm"] != pcm:
             c = min(chunk, b)
             st = self._pipe = {
-                "chunk": c, "h2d": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
-                "audio": [torch.empty((c, audio_h.shape[1]), device=dev) for _ in range(2)],
+                "chunk": c, "pcm": pcm, "h2d": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
+                "audio": [torch.empty((c, audio_h.shape[1]), dtype=audio_h.dtype, device=dev) for _ in range(2)],
+                "audio_f32": torch.empty((c, audio_h.shape[1]), device=dev) if pcm else None,
                 "prior": [torch.empty((c, cfg.prior_frames, cfg.pose_dim), device=dev) for _ in range(2)],
                 "out": [(torch.empty((c, cfg.frames, cfg.pose_dim), device=dev),
                          torch.empty((c, cfg.frames, cfg.d_model), device=dev),
@@ -241,7 +256,10 @@ class Engine:
             main.wait_event(st["ready"][slot])
             if used[slot]:
                 main.wait_event(st["out_free"][slot])
-            spec = self.logmel(st["audio"][slot][:n], mode, preemph)
+            a_dev = st["audio"][slot][:n]
+            if pcm:        # the staging slot is free again as soon as the samples are widened
+                a_dev = self.pcm16_to_float(a_dev, st["audio_f32"][:n])
+            spec = self.logmel(a_dev, mode, preemph)
             out = tuple(t[:n] for t in st["out"][slot])
             self.generator_forward(spec, st["prior"][slot][:n], None, out=out)
             if poses_dev is not None:
@@ -267,6 +285,8 @@ class Engine:
     def _infer_host_whole(self, audio_h, prior_h, poses_h, mode, preemph, poses_dev):
         dev = self.device
         audio = audio_h.to(dev, non_blocking=True)
+        if audio.dtype == torch.int16:
+            audio = self.pcm16_to_float(audio)
         prior = prior_h.to(dev, non_blocking=True)
         poses = self.generator_forward(self.logmel(audio, mode, preemph), prior)[0]
         if poses_dev is not None:

@@ -91,6 +91,12 @@ EGX_API int  egx_finalize_weights(egx_handle* h);
 EGX_API int  egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols,
                 int mode, int preemph, float* out, void* stream);
 
+/* 16-bit PCM samples -> float32 in [-1, 1) (x / 32768, exact: the scaling every wav decoder applies).  No counterpart
+ * in the reference, whose LMDB holds clips that were decoded offline (data_loader/data_preprocessor_expressive.py:73,
+ * 'audio_raw'); an extension for serving raw speech, so that it crosses PCIe at 2 bytes per sample and is widened on the
+ * device.  pcm, out: device pointers, n_samples elements. */
+EGX_API int  egx_audio_pcm16_to_f32(egx_handle* h, const int16_t* pcm, int64_t n_samples, float* out, void* stream);
+
 /* Replaces: make_audio_fixed_length (utils/data_utils.py:69-75) for a ragged batch.  Clip b is
  * samples[offsets[b] .. offsets[b+1]) (f32 / int64, both device memory, n_clips + 1 offsets); every clip is cropped
  * to n_out samples or extended at its end the way np.pad(mode='symmetric') does -> out (n_clips, n_out) f32, the

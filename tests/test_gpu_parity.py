@@ -327,6 +327,29 @@ def test_infer_host_pipeline_matches_single_shot():
     assert torch.equal(poses_h, ref)
 
 
+def test_infer_host_pcm16_and_streaming_join():
+    """int16 PCM input is widened on the device exactly like a wav decoder does on the host (x / 32768), so the poses
+    equal those of the float path on the same samples bit for bit; `join=False` + `host_join()` (the streaming form:
+    the next call's kernels do not queue behind this call's last copy) delivers the same poses."""
+    eng, _ = _engine("ted", 0, "tc")
+    n = 13
+    pcm = torch.from_numpy((synth.synth_audio(n, TED.n_audio, seed=8) * 32767.0).round().astype(np.int16)).pin_memory()
+    as_float = (pcm.to(torch.float32) / 32768.0).pin_memory()
+    assert torch.equal(eng.pcm16_to_float(pcm.cuda()).cpu(), as_float)
+    prior = torch.from_numpy(synth.synth_prior(n, TED.prior_frames, TED.pose_dim, 8)).pin_memory()
+    ref = torch.empty(n, TED.frames, TED.pose_dim).pin_memory()
+    eng.infer_host(as_float, prior, ref, chunk=5, mode=LOGMEL_LOG_IN, preemph=True)
+    torch.cuda.synchronize()
+    got = torch.empty_like(ref).pin_memory()
+    for _ in range(3):                                   # staging slots alternate across calls
+        eng.infer_host(pcm, prior, got, chunk=5, mode=LOGMEL_LOG_IN, preemph=True, join=False)
+    eng.host_join()
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(got, ref)
+    with pytest.raises(RuntimeError, match="float32 or int16"):
+        eng.infer_host(as_float.double().pin_memory(), prior, got)
+
+
 def test_infer_host_keeps_the_batch_whole_for_the_memory_generator():
     """Models_memory.Transformer couples the clips of one call (Models_memory.py:287-288): the chunked host entry must
     not cut that batch — its poses equal forward() on the whole batch, not on chunks."""
