@@ -1497,7 +1497,7 @@ int egx_logmel(egx_handle* h, const float* audio, int n_clips, int n_samples, in
 }
 
 // Test hook: the same front end through the kernel that keeps the (128, n_cols) tile in global memory (the path of
-// spectrograms wider than 96 columns), whatever the width: the two kernels must agree bit for bit.
+// spectrograms too wide for two shared-memory tiles per SM), whatever the width: the two kernels must agree bit for bit.
 int egx_debug_logmel_global_tile(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols, int mode,
                                  int preemph, float* out, void* stream) {
     return logmel_checked(h, audio, n_clips, n_samples, n_cols, mode, preemph, out, stream, true);

@@ -237,7 +237,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Round-2 variant for tiles that fit in shared memory next to the FFT buffers (n_cols <= kTileMaxCols): the SAME
+// Round-2 variant for tiles that fit in shared memory next to the FFT buffers twice per SM (kTileMaxSmem): the SAME
 // arithmetic in the same order (bit-identical output), restructured around what bounded the kernel above — the L1/shared
 // pipe (82% busy: 658 shared wavefronts + 437 global tag requests per frame) —
 //   * the frame goes from global memory straight into the registers of the first radix-8 pass (no staging round trip);
@@ -249,7 +249,7 @@ logmel_kernel(const float* __restrict__ audio, int N, int n_cols, int mode, int 
 //   * the (128, n_cols) tile lives in shared memory: the transposed per-frame writes (32 lines per store) and the two
 //     re-reads for the statistics never leave the SM, the normalised tile is written once, coalesced.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kTileMaxCols = 96;
+constexpr size_t kTileMaxSmem = 113 * 1024;      // two CTAs per SM
 __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 15); }
 
 // one complex point (two samples) of a frame with every check of the general path
@@ -495,9 +495,9 @@ int launch_logmel(const LogmelTables& t, const float* audio, int B, int N, int n
     int warps = kMaxWarps;
     for (int w = kMaxWarps; w >= 9; --w)
         if ((n_cols + w - 1) / w * w < (n_cols + warps - 1) / warps * warps) warps = w;
-    const bool tile = !force_global_tile && env_switch("EGX_LOGMEL_TILE", g_logmel_tile) && n_cols <= kTileMaxCols;
-    const size_t smem = tile ? sizeof(float2) * warps * (kHalf + 8) + sizeof(float) * kMels * (size_t)(n_cols | 1)
-                             : sizeof(float2) * warps * kBufLen;
+    const size_t smem_tile = sizeof(float2) * warps * (kHalf + 8) + sizeof(float) * kMels * (size_t)(n_cols | 1);
+    const bool tile = !force_global_tile && env_switch("EGX_LOGMEL_TILE", g_logmel_tile) && smem_tile <= kTileMaxSmem;
+    const size_t smem = tile ? smem_tile : sizeof(float2) * warps * kBufLen;
     // opt-in shared-memory size is a per-device function attribute (one handle per device may live in one process)
     static size_t configured[2][64] = {};
     int dev = 0;

@@ -219,7 +219,7 @@ EGX_API int  egx_debug_ffn_tc(egx_handle* h, const float* x, const float* w1, co
                       void* out16, void* stream);
 
 /* Test hook of the front end: egx_logmel through the kernel that keeps the (128, n_cols) tile in global memory (the
- * path of spectrograms wider than 96 columns) whatever the width.  Both kernels run the same arithmetic in the same
+ * path of spectrograms too wide for two shared-memory tiles per SM, about 140 columns) whatever the width.  Both kernels run the same arithmetic in the same
  * order: tests require bit-identical outputs. */
 EGX_API int  egx_debug_logmel_global_tile(egx_handle* h, const float* audio, int n_clips, int n_samples, int n_cols,
                                   int mode, int preemph, float* out, void* stream);

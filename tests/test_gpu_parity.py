@@ -88,11 +88,11 @@ def test_logmel_no_preemph_and_ragged_cols():
 @pytest.mark.parametrize("mode,preemph", [(LOGMEL_LOG_IN, True), (LOGMEL_LOG_IN, False), (LOGMEL_DB, False),
                                           (LOGMEL_REFERENCE, False), (LOGMEL_DB, True)])
 def test_logmel_tile_kernels_agree_bitwise(mode, preemph):
-    """K1 has two kernels (tile in shared memory for n_cols <= 96, tile in global memory above): same arithmetic in the same
+    """K1 has two kernels (tile in shared memory while two CTAs fit per SM, tile in global memory above): same arithmetic in the same
     order, so identical bits — for even and odd clip starts (N odd: every other clip is misaligned for 8-byte loads),
     clips shorter than a frame, ragged widths, and a batch view that starts on an odd float."""
     eng, _ = _engine("ted", 0, "fp32")
-    for n, cols, b in ((36267, 70, 5), (36268, 70, 3), (5000, 7, 4), (700, 2, 3), (36267, 1, 2), (48000, 94, 2)):
+    for n, cols, b in ((36267, 70, 5), (36268, 70, 3), (5000, 7, 4), (700, 2, 3), (36267, 1, 2), (48000, 94, 2), (64000, 124, 3)):
         audio = torch.from_numpy(synth.synth_audio(b, n, seed=n % 97)).cuda()
         a = eng.logmel(audio, mode, preemph, n_cols=cols)
         g = eng.logmel(audio, mode, preemph, n_cols=cols, _global_tile=True)
