@@ -296,6 +296,11 @@ logmel_tile_kernel(const float* __restrict__ audio, int N, int n_cols, int mode,
     // the clip's first sample sits on an even float of the address space (8-byte loads of sample pairs); uniform per CTA
     const bool aligned = (((reinterpret_cast<uintptr_t>(audio) >> 2) + (size_t)blockIdx.x * N) & 1) == 0;
 
+    // pass-2 twiddles W64^((j & 7) t): the same for j = lane and lane + 32, and for every frame — registers
+    float2 tw2[7];
+#pragma unroll
+    for (int tt = 1; tt < 8; ++tt) tw2[tt - 1] = __ldg(&tw512[tt * 64 + lane]);
+
     for (int t = warp; t < n_cols; t += n_warps) {
         const int base = t * kHop - kFFT / 2;
         // interior frame: every sample (and the one before the frame) exists, and no sample is the clip's first.  A clip
@@ -355,7 +360,9 @@ logmel_tile_kernel(const float* __restrict__ audio, int N, int n_cols, int mode,
             const int j = lane + 32 * h2;
 #pragma unroll
             for (int tt = 0; tt < 8; ++tt) a[h2][tt] = buf[swz(j + 64 * tt)];
-            twiddle_dft8<8>(a[h2], j, tw512);
+#pragma unroll
+            for (int tt = 1; tt < 8; ++tt) a[h2][tt] = cmul(a[h2][tt], tw2[tt - 1]);
+            dft8(a[h2]);
         }
         __syncwarp();
 #pragma unroll
