@@ -38,6 +38,20 @@ template <> struct Vec4<__half> {
     }
 };
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 — two independent IEEE fp32 FMAs per issued instruction, bit-identical to two
+// FFMAs): the CUDA-core kernels here are instruction-issue bound, not FMA-pipe bound
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------------------------------
 // K2 stem.  spec (B,H,W) fp32 -> out (B,H,W,32) T.  Persistent CTAs walk (clip, 32-row strip) items.  A thread
 // owns 8 output channels whose 72 weights + bias / BN affine stay in registers for the whole kernel; the strip's
@@ -56,21 +70,27 @@ stem_kernel(const float* __restrict__ spec, int H, int W, int strips, int n_item
     const int PW = W + 2;
     const int n_stage = (kStemRows + 2) * PW;
     const int cg = threadIdx.x & 3;                        // channels [8*cg, 8*cg + 8)
-    float wr[8][9], br[8], sr[8], tr[8];
+    // weights and bias as channel PAIRS (2p, 2p + 1) for the packed FMAs
+    uint64_t wr2[4][9], br2[4];
+    float sr[8], tr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
+    for (int p2 = 0; p2 < 4; ++p2) {
+        const int c = cg * 8 + 2 * p2;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wr[j][k] = w[c * 9 + k];
-        br[j] = bias[c]; sr[j] = scale[c]; tr[j] = shift[c];
+        for (int k = 0; k < 9; ++k) wr2[p2][k] = pack2(w[c * 9 + k], w[(c + 1) * 9 + k]);
+        br2[p2] = pack2(bias[c], bias[c + 1]);
+        sr[2 * p2] = scale[c]; sr[2 * p2 + 1] = scale[c + 1];
+        tr[2 * p2] = shift[c]; tr[2 * p2 + 1] = shift[c + 1];
     }
     // pin the 96 parameters in registers (otherwise the compiler re-reads them from global memory inside the loop)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int p2 = 0; p2 < 4; ++p2) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) asm volatile("" : "+f"(wr[j][k]));
-        asm volatile("" : "+f"(br[j]), "+f"(sr[j]), "+f"(tr[j]));
+        for (int k = 0; k < 9; ++k) asm volatile("" : "+l"(wr2[p2][k]));
+        asm volatile("" : "+l"(br2[p2]));
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("" : "+f"(sr[j]), "+f"(tr[j]));
     // stage the padded strip of `item` into buffer sb with 4-byte cp.async copies (src-size 0 = zero fill for the padding)
     auto stage = [&](int item, float* sb) {
         const int b = item / strips, y0 = (item - b * strips) * kStemRows;
@@ -96,18 +116,24 @@ stem_kernel(const float* __restrict__ spec, int H, int W, int strips, int n_item
         int ly = 0, x = threadIdx.x >> 2;
         while (x >= W) { x -= W; ++ly; }
         for (; ly < rows;) {
-            float tap[9];
+            uint64_t tap2[9];                               // (tap, tap)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) tap[dy * 3 + dx] = sb[(ly + dy) * PW + x + dx];
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float t = sb[(ly + dy) * PW + x + dx];
+                    tap2[dy * 3 + dx] = pack2(t, t);
+                }
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float acc = br[j];
+            for (int p2 = 0; p2 < 4; ++p2) {
+                uint64_t acc = br2[p2];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) acc = fmaf(wr[j][k], tap[k], acc);
-                v[j] = fmaxf(acc, 0.f) * sr[j] + tr[j];
+                for (int k = 0; k < 9; ++k) acc = fma2(wr2[p2][k], tap2[k], acc);    // same order as the scalar loop
+                float a0, a1;
+                unpack2(acc, a0, a1);
+                v[2 * p2] = fmaxf(a0, 0.f) * sr[2 * p2] + tr[2 * p2];
+                v[2 * p2 + 1] = fmaxf(a1, 0.f) * sr[2 * p2 + 1] + tr[2 * p2 + 1];
             }
             T* o = out + (((size_t)b * H + y0 + ly) * W + x) * 32 + cg * 8;
             const float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
