@@ -346,6 +346,14 @@ def test_infer_host_pcm16_and_streaming_join():
     eng.host_join()
     torch.cuda.current_stream().synchronize()
     assert torch.equal(got, ref)
+    # graph=True: each staging slot replays a captured CUDA graph (single-chunk calls), float and PCM inputs
+    for src in (as_float, pcm):
+        got.zero_()
+        for _ in range(3):
+            eng.infer_host(src, prior, got, chunk=n, mode=LOGMEL_LOG_IN, preemph=True, join=False, graph=True)
+        eng.host_join()
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(got, ref)
     with pytest.raises(RuntimeError, match="float32 or int16"):
         eng.infer_host(as_float.double().pin_memory(), prior, got)
 
