@@ -310,12 +310,29 @@ def run_generator(args, name):
     free = [torch.cuda.Event() for _ in range(2)]
     state = {"i": 0, "used": [False, False]}
 
+    # --gather peer (default): copy-engine pushes into every rank's buffer over NVLink (sharding.PeerGather) — no SMs
+    # taken from the persistent compute kernels it overlaps; --gather nccl: one all_gather_into_tensor
+    peer = None
+    if world > 1 and args.gather == "peer":
+        from emotiongestures_b200.sharding import PeerGather
+        try:
+            peer = PeerGather(B * cfg.frames * cfg.pose_dim, torch.float32, dev)
+            gathered = [b.view(world * B, cfg.frames, cfg.pose_dim) for b in peer.bufs]
+        except Exception as e:                                  # no CUDA IPC in this container: say so, use NCCL
+            print(f"[bench] peer gather unavailable ({type(e).__name__}: {e}); using the NCCL all-gather", file=sys.stderr)
+            peer = None
+        if peer is None:
+            gathered = [torch.empty(world * B, cfg.frames, cfg.pose_dim, device=dev) for _ in range(2)]
+
     def gather_async(poses, slot):
         main = torch.cuda.current_stream(dev)
         done[slot].record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(done[slot])
-            dist.all_gather_into_tensor(gathered[slot].view(-1), poses.reshape(-1))
+            if peer is not None:
+                peer.gather(poses.reshape(-1), slot, comm)
+            else:
+                dist.all_gather_into_tensor(gathered[slot].view(-1), poses.reshape(-1))
             free[slot].record(comm)
         state["used"][slot] = True
 
@@ -476,7 +493,17 @@ def run_generator(args, name):
             fgd_leg["identical_on_all_ranks"] = bool((lo == hi).item())
             buf = torch.empty(world * B, cfg.frames, cfg.pose_dim, device=dev)
             ms_ag = d.timed(lambda: dist.all_gather_into_tensor(buf.view(-1), poses.reshape(-1)), 20, 3)
-            collectives = {"pose_all_gather_ms": ms_ag, "pose_bytes_per_rank": poses.numel() * 4,
+            ms_pg = None
+            if peer is not None:
+                cur = torch.cuda.current_stream(dev)
+                ms_pg = d.timed(lambda: peer.gather(poses.reshape(-1), 0, cur), 20, 3)
+                same = torch.tensor([int(torch.equal(peer.bufs[0], buf.view(-1)))], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                if not same.item():
+                    raise SystemExit("peer gather and NCCL all-gather disagree")
+            collectives = {"pose_gather": "peer copies on the copy engines + 4-byte all-reduce" if peer is not None else "nccl all_gather_into_tensor",
+                           "pose_peer_gather_ms": ms_pg,
+                           "pose_all_gather_ms": ms_ag, "pose_bytes_per_rank": poses.numel() * 4,
                            "pose_bytes_received_per_rank": poses.numel() * 4 * (world - 1),
                            "fgd_all_reduce_ms": ms_ar, "fgd_bytes": acc.numel() * 8,
                            "overlap": "the gather of step i runs on a side stream under the kernels of step i + 1"}
@@ -563,7 +590,7 @@ def run_generator(args, name):
                          "f16" if args.precision == "tc" else "f32",
                          {"workload": spec_["workload"], "clips_per_gpu": B, "global_batch": B * world,
                           "precision": args.precision, "logmel": "preemph+log+InstanceNorm (F4b)",
-                          "parallelism": f"dp{world} (clip-sharded; pose all_gather_into_tensor on a side stream)",
+                          "parallelism": f"dp{world} (clip-sharded; pose gather on a side stream: " + ("peer copies over NVLink" if peer is not None else "NCCL all_gather_into_tensor") + ")",
                           "l2": "inputs larger than L2 (%.0f MB audio per step)" % (audio.numel() * 4 / 1e6),
                           "host_numa_node_rank0": d.numa_node})
         line.update({
@@ -922,6 +949,7 @@ def main():
     # clips per pipeline chunk of Engine.infer_host.  Measured on one box against the device-resident value: 1024 -> 0.93,
     # 2048 -> 0.965, 4096 (= the whole step: step k+1's host->device copy runs under step k's kernels, step k's
     # device->host copy under step k+1's) -> 0.995
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--e2e-chunk", type=int, default=4096)
     # one CUDA-graph replay per staging slot inside infer_host instead of ~110 launches: measured equal at N = 1 and N = 8
     # (884k vs 876k end to end on eight GPUs: the gap to the device-resident value there is the PCIe fabric, not launches)

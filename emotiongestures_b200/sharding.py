@@ -49,6 +49,60 @@ def all_gather_poses(local: torch.Tensor, n_clips: int, group=None) -> torch.Ten
     return torch.cat(parts, dim=0)
 
 
+class PeerGather:
+    """All-gather of equal-size shards by peer-to-peer copies over NVLink on the COPY ENGINES: the destination buffers
+    are symmetric memory (torch.distributed._symmetric_memory: cuMem allocations exported to every rank of the node),
+    every rank pushes its shard into all of them with plain device-to-device copies (measured 715 GB/s per push on
+    B200 / NV18), and a 4-byte all-reduce behind the pushes is the completion barrier.  An NCCL all-gather of the same
+    bytes runs as a kernel on a dozen SMs for its whole duration, and this path's compute kernels are persistent with
+    one CTA per SM: whenever the gather of step i overlaps the kernels of step i + 1, those kernels wait for the SMs
+    NCCL holds.  Copy-engine pushes take no SM at all.  (Legacy cudaIpc mappings — torch.multiprocessing's
+    reduce_tensor — were measured first: 25 GB/s per push across processes in this environment, i.e. staged through
+    the host; not used.)
+
+    `slots` destination buffers alternate between calls (the gather of one step overlaps the next step's compute).
+    `gather(shard, slot, stream, consumed=None)`: enqueue on `stream`; returns this rank's (world * shard_numel,) buffer
+    of that slot, valid once `stream` has run past the call.  `consumed`: event recorded after this rank finished
+    READING that slot the last time round — peers overwrite it two calls later, and the barrier of the call in between
+    is what holds them back until every rank has passed its `consumed` event."""
+
+    def __init__(self, shard_numel: int, dtype, device, slots: int = 2, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group, self.n, self.slots = group, int(shard_numel), slots
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
+        name = (group or dist.group.WORLD).group_name
+        self.bufs, self.peer, err = [], [[] for _ in range(self.world)], None
+        try:
+            for _ in range(slots):
+                buf = symm_mem.empty(self.world * self.n, dtype=dtype, device=self.device)
+                hdl = symm_mem.rendezvous(buf, name)
+                self.bufs.append(buf)
+                for r in range(self.world):
+                    self.peer[r].append(buf if r == self.rank else hdl.get_buffer(r, (self.world * self.n,), dtype))
+        except Exception as e:             # no symmetric memory here: fail on EVERY rank, not on one
+            err = e
+        self._token = torch.zeros(1, device=self.device)
+        ok = torch.tensor([0 if err else 1], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not ok.item():
+            raise RuntimeError(f"PeerGather: symmetric memory is not available on every rank ({err})")
+
+    def gather(self, shard: torch.Tensor, slot: int, stream=None, consumed=None) -> torch.Tensor:
+        if shard.numel() != self.n or shard.dtype != self.bufs[0].dtype or not shard.is_contiguous():
+            raise RuntimeError("shard must be contiguous with the size and dtype given at construction")
+        stream = stream or torch.cuda.current_stream(self.device)
+        flat = shard.reshape(-1)
+        with torch.cuda.stream(stream):
+            if consumed is not None:
+                stream.wait_event(consumed)
+            for k in range(self.world):
+                r = (self.rank + k) % self.world                      # spread the targets: no two ranks start on the same peer
+                self.peer[r][slot][self.rank * self.n:(self.rank + 1) * self.n].copy_(flat, non_blocking=True)
+            dist.all_reduce(self._token, group=self.group)             # nobody gets past it before everybody's pushes are done
+        return self.bufs[slot]
+
+
 def bind_host_to_gpu_node(device_index: int):
     """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated
     afterwards (first-touch placement) sit next to that GPU's PCIe root: with one process per GPU streaming ~600 MB per

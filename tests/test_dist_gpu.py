@@ -23,7 +23,7 @@ def _worker(rank, world, port, n_clips, q):
     import torch.distributed as dist
     from emotiongestures_b200 import LOGMEL_LOG_IN, TED, fgd
     from emotiongestures_b200.engine import Engine
-    from emotiongestures_b200.sharding import all_gather_poses, shard_bounds
+    from emotiongestures_b200.sharding import PeerGather, all_gather_poses, shard_bounds
     from oracle import synth
     from tests.helpers import model_and_sd
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -47,7 +47,20 @@ def _worker(rank, world, port, n_clips, q):
         eng.fgd_accumulate(feats[lo:hi], acc, shift)
         fgd.all_reduce_stats(acc)
         mu, sigma = fgd.finalize_stats(acc, 64, shift)
-        q.put((rank, bool(torch.equal(gathered, whole)), whole.cpu().numpy(), mu, sigma))
+        # the copy-engine gather (equal shards): same bytes as the NCCL all-gather, several rounds over both slots
+        peer_ok = True
+        if n_clips % world == 0:
+            pg = PeerGather(local.numel(), local.dtype, dev)
+            comm = torch.cuda.Stream(dev)
+            for it in range(4):
+                shard = (local + float(it)).contiguous()
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+                comm.wait_event(ready)
+                full = pg.gather(shard, it & 1, comm)
+                comm.synchronize()
+                peer_ok &= bool(torch.equal(full.view(n_clips, *local.shape[1:]), whole + float(it)))
+        q.put((rank, bool(torch.equal(gathered, whole)) and peer_ok, whole.cpu().numpy(), mu, sigma))
     finally:
         dist.destroy_process_group()
 
