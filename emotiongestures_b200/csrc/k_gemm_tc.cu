@@ -98,33 +98,6 @@ struct GemmTcEpi {
 
 __device__ __forceinline__ void gemm_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// 32 columns of one output row: fp32 and / or fp16 copies with 256-bit stores (ld32 % 8 == 0, ld16 % 16 == 0, 32-byte
-// aligned bases: what the LN variant requires of its callers)
-__device__ __forceinline__ void store_chunk32(const float (&v)[32], float* o32, __half* o16) {
-    if (o32) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o32 + 8 * j), "f"(v[8 * j]),
-                         "f"(v[8 * j + 1]), "f"(v[8 * j + 2]), "f"(v[8 * j + 3]), "f"(v[8 * j + 4]), "f"(v[8 * j + 5]),
-                         "f"(v[8 * j + 6]), "f"(v[8 * j + 7])
-                         : "memory");
-    }
-    if (o16) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            uint32_t u[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const __half2 h2 = __floats2half2_rn(v[16 * j + 2 * e], v[16 * j + 2 * e + 1]);
-                u[e] = *reinterpret_cast<const uint32_t*>(&h2);
-            }
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o16 + 16 * j), "r"(u[0]), "r"(u[1]),
-                         "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
-                         : "memory");
-        }
-    }
-}
-
 template <int BN, bool RES, bool LN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
